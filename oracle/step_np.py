@@ -1,0 +1,456 @@
+"""Self-contained numpy restatement of the reference hot path (TEST INFRASTRUCTURE).
+
+Travels to the GPU box (no /root/reference there).  Each function cites the reference
+lines it follows; paths are relative to /root/reference/fluidsim.  Pinned here, in the
+build container, against the reference's own modules executed through
+``oracle.refshim`` (``tests/test_oracle_vs_reference.py``; fixtures in ``tests/golden``
+made by ``tests/golden/make_golden.py``).  The fluidfft layer underneath
+(``oracle.fluidfft_np``) is a restatement of an absent third-party dependency:
+parity of that layer is UNPINNED (see ``oracle/__init__.py``).
+"""
+
+from math import pi
+
+import numpy as np
+
+from .fluidfft_np import (
+    OperatorsPseudoSpectral2D,
+    OperatorsPseudoSpectral3D,
+    SetOfVariables,
+    vector_product,
+)
+
+
+# ------------------------------------------------------------------ operators (fluidsim level)
+def reinit_truncation(oper, truncation_shape, ndim):
+    """operators/base.py:47-72 (``OperatorBase._reinit_truncation``)."""
+    if truncation_shape == "cubic":
+        return
+    kmax = oper.coef_dealiasing * oper.deltakx * oper.nx / 2
+    if truncation_shape == "spherical":
+        oper.where_dealiased = np.array(oper.K2 >= kmax**2, dtype=np.uint8)
+    elif truncation_shape == "no_multiple_aliases":
+        # operators3d.py:280-288 / operators2d.py:195-198
+        ax = abs(oper.Kx if ndim == 3 else oper.KX) >= 2 / 3 * oper.deltakx * oper.nx / 2
+        ay = abs(oper.Ky if ndim == 3 else oper.KY) >= 2 / 3 * oper.deltaky * oper.ny / 2
+        if ndim == 3:
+            az = abs(oper.Kz) >= 2 / 3 * oper.deltakz * oper.nz / 2
+            where = (ax & ay) | (ay & az) | (az & ax)
+        else:
+            where = ax & ay
+        if oper.coef_dealiasing:
+            where |= oper.K2 >= kmax**2
+        oper.where_dealiased = np.array(where, dtype=np.uint8)
+    else:
+        raise ValueError(
+            'truncation_shape must be "cubic", "spherical" or "no_multiple_aliases"'
+        )
+
+
+def dealiasing_setofvar(sov, where_dealiased):
+    """operators3d.py:38-59,74-76 (numpy variant ``dealiasing_setofvar_numpy``)."""
+    nz = np.nonzero(where_dealiased)
+    for i in range(sov.shape[0]):
+        sov[i][nz] = 0.0
+
+
+# ------------------------------------------------------------------ time-stepping kernels
+def step_Euler(state_spect, dt, tendencies, diss, output):
+    """base/time_stepping/pseudo_spect.py:51-56."""
+    output[:] = (state_spect + dt * tendencies) * diss
+    return output
+
+
+def step_like_RK2(state_spect, dt, tendencies, diss, diss2):
+    """base/time_stepping/pseudo_spect.py:64-68."""
+    state_spect[:] = state_spect * diss + dt * diss2 * tendencies
+
+
+class OracleSim:
+    """ns3d | ns3d.strat | ns2d simulation object reduced to its hot path.
+
+    Mirrors the construction order of ``base/solvers/base.py:117-223`` and the per-step
+    sequence of ``solvers/ns3d/time_stepping.py:8-20`` /
+    ``base/time_stepping/pseudo_spect.py:236-243``.
+    """
+
+    def __init__(
+        self,
+        solver,
+        nx,
+        ny,
+        nz=None,
+        Lx=2 * pi,
+        Ly=2 * pi,
+        Lz=2 * pi,
+        nu_2=0.0,
+        nu_4=0.0,
+        nu_8=0.0,
+        nu_m4=0.0,
+        coef_dealiasing=2.0 / 3,
+        truncation_shape="cubic",
+        type_time_scheme="RK4",
+        deltat0=1e-2,
+        N=1.0,
+        f=None,
+        beta=0.0,
+    ):
+        self.solver = solver
+        self.nu_2, self.nu_4, self.nu_8, self.nu_m4 = nu_2, nu_4, nu_8, nu_m4
+        self.N, self.f, self.beta = N, f, beta
+        self.deltat = float(deltat0)
+        self.scheme = type_time_scheme
+        self.it = 0
+        self.t = 0.0
+        if solver == "ns2d":
+            self.ndim = 2
+            self.oper = OperatorsPseudoSpectral2D(nx, ny, Lx, Ly, coef_dealiasing=coef_dealiasing)
+            self.oper.Lx, self.oper.Ly = self.oper.lx, self.oper.ly
+            keys_spect = ["rot_fft"]
+            keys_phys = ["ux", "uy", "rot"]
+        elif solver in ("ns3d", "ns3d.strat"):
+            self.ndim = 3
+            self.oper = OperatorsPseudoSpectral3D(
+                nx, ny, nz, Lx, Ly, Lz, coef_dealiasing=coef_dealiasing
+            )
+            keys_phys = ["vx", "vy", "vz"] + (["b"] if solver == "ns3d.strat" else [])
+            keys_spect = [k + "_fft" for k in keys_phys]
+        else:
+            raise ValueError(solver)
+        reinit_truncation(self.oper, truncation_shape, self.ndim)
+        oper = self.oper
+        # base/state.py:243-248, 63-68
+        self.state_spect = SetOfVariables(
+            keys=keys_spect, shape_variable=oper.shapeK_loc, dtype=np.complex128, info="state_spect"
+        )
+        self.state_phys = SetOfVariables(
+            keys=keys_phys, shape_variable=oper.shapeX_loc, dtype=np.float64, info="state_phys"
+        )
+        self.state_spect[:] = 0
+        self.state_phys[:] = 0
+        n_tmp = 4 if self.ndim == 2 else 6  # ns2d/state.py:43-46, ns3d/state.py:46-52
+        self.fields_tmp = tuple(np.empty(oper.shapeX_loc) for _ in range(n_tmp))
+        self.fields_spect_tmp = tuple(
+            np.empty(oper.shapeK_loc, dtype=np.complex128) for _ in range(3)
+        )
+        # pseudo_spect.py:179-189, 103-152
+        self.freq_lin = self.compute_freq_diss()
+        self.exact = np.exp(-self.deltat * self.freq_lin)
+        self.exact2 = np.exp(-self.deltat / 2 * self.freq_lin)
+        self._state_spect_tmp = np.empty_like(self.state_spect)
+        self._state_spect_tmp1 = np.empty_like(self.state_spect)
+
+    # ------------------------------------------------------------------ linear term
+    def compute_freq_diss(self):
+        """base/solvers/pseudo_spect.py:134-191."""
+        oper = self.oper
+        if self.nu_2 > 0:
+            f_d = self.nu_2 * oper.K2
+        else:
+            f_d = np.zeros_like(oper.K2)
+        if self.nu_4 > 0.0:
+            f_d += self.nu_4 * oper.K2**2
+        if self.nu_8 > 0.0:
+            f_d += self.nu_8 * oper.K8
+        if self.nu_m4 != 0.0:
+            K2_not0 = np.copy(oper.K2)
+            K2_not0[(0,) * self.ndim] = 1e-14
+            f_d_hypo = self.nu_m4 / K2_not0**2
+            if self.ndim == 2:
+                f_d_hypo[0, 0] = f_d_hypo[0, 1]
+            else:
+                f_d_hypo[0, 0, 0] = f_d_hypo[0, 0, 1]
+        else:
+            f_d_hypo = 0.0
+        return f_d + f_d_hypo
+
+    def set_deltat(self, dt):
+        """ExactLinearCoefs.compute, pseudo_spect.py:122-141."""
+        self.deltat = float(dt)
+        self.exact = np.exp(-dt * self.freq_lin)
+        self.exact2 = np.exp(-dt / 2 * self.freq_lin)
+
+    # ------------------------------------------------------------------ state sync
+    def statephys_from_statespect(self):
+        """base/state.py:326-332; ns2d/state.py:95-106."""
+        oper = self.oper
+        if self.ndim == 2:
+            rot_fft = self.state_spect.get_var("rot_fft")
+            ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
+            oper.ifft_as_arg(rot_fft, self.state_phys.get_var("rot"))
+            oper.ifft_as_arg(ux_fft, self.state_phys.get_var("ux"))
+            oper.ifft_as_arg(uy_fft, self.state_phys.get_var("uy"))
+        else:
+            for ik in range(self.state_spect.nvar):
+                oper.ifft_as_arg(self.state_spect[ik].view(np.ndarray), self.state_phys[ik].view(np.ndarray))
+
+    def set_state_spect(self, arr):
+        self.state_spect[...] = arr
+        self.statephys_from_statespect()
+
+    # ------------------------------------------------------------------ nonlinear terms
+    def project_state_spect(self, state_spect):
+        """solvers/ns3d/solver.py:255-263 (projection=None, no_vz_kz0=False)."""
+        self.oper.project_perpk3d(
+            state_spect.get_var("vx_fft"), state_spect.get_var("vy_fft"), state_spect.get_var("vz_fft")
+        )
+
+    def dealiasing(self, thing):
+        """operators3d.py:336-342; operators2d.py:200-220."""
+        oper = self.oper
+        if self.ndim == 2 and not oper._has_to_dealiase:
+            return
+        if isinstance(thing, SetOfVariables):
+            dealiasing_setofvar(thing, oper.where_dealiased)
+        else:
+            thing[np.nonzero(oper.where_dealiased)] = 0.0
+
+    def tendencies_nonlin(self, state_spect=None, old=None):
+        if self.solver == "ns2d":
+            return self._tendencies_ns2d(state_spect, old)
+        return self._tendencies_ns3d(state_spect, old)
+
+    def _tendencies_ns3d(self, state_spect=None, old=None):
+        """solvers/ns3d/solver.py:180-253; strat extras solvers/ns3d/strat/solver.py:138-216."""
+        oper = self.oper
+        strat = self.solver == "ns3d.strat"
+        get = (self.state_spect if state_spect is None else state_spect).get_var
+        vx_fft, vy_fft, vz_fft = get("vx_fft"), get("vy_fft"), get("vz_fft")
+        omegax_fft, omegay_fft, omegaz_fft = self.fields_spect_tmp
+        oper.rotfft_from_vecfft_outin(vx_fft, vy_fft, vz_fft, omegax_fft, omegay_fft, omegaz_fft)
+        if self.f is not None:
+            omegaz_fft[0, 0, 0] += self.f  # solver.py:176-178
+        omegax, omegay, omegaz = self.fields_tmp[3:6]
+        oper.ifft_as_arg_destroy(omegax_fft, omegax)
+        oper.ifft_as_arg_destroy(omegay_fft, omegay)
+        oper.ifft_as_arg_destroy(omegaz_fft, omegaz)
+        if state_spect is None:
+            vx = self.state_phys.get_var("vx")
+            vy = self.state_phys.get_var("vy")
+            vz = self.state_phys.get_var("vz")
+        else:
+            vx, vy, vz = self.fields_tmp[0:3]
+            oper.ifft_as_arg(vx_fft, vx)
+            oper.ifft_as_arg(vy_fft, vy)
+            oper.ifft_as_arg(vz_fft, vz)
+        fx, fy, fz = vector_product(vx, vy, vz, omegax, omegay, omegaz)
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state_spect, info="tendencies_nonlin")
+        else:
+            tendencies_fft = old
+        oper.fft_as_arg(fx, tendencies_fft.get_var("vx_fft"))
+        oper.fft_as_arg(fy, tendencies_fft.get_var("vy_fft"))
+        oper.fft_as_arg(fz, tendencies_fft.get_var("vz_fft"))
+        if strat:
+            b_fft = get("b_fft")
+            fz_fft = tendencies_fft.get_var("vz_fft")
+            fz_fft += b_fft  # strat/solver.py:198
+            if state_spect is None:
+                b = self.state_phys.get_var("b")
+            else:
+                b = self.fields_tmp[3]
+                oper.ifft_as_arg(b_fft, b)
+            div_vb_fft = oper.div_vb_fft_from_vb(vx, vy, vz, b)
+            # compute_fb_fft, strat/solver.py:29-33
+            fb_fft = -div_vb_fft - self.N**2 * vz_fft
+            tendencies_fft.set_var("b_fft", fb_fft)
+        self.project_state_spect(tendencies_fft)
+        self.dealiasing(tendencies_fft)
+        return tendencies_fft
+
+    def _tendencies_ns2d(self, state_spect=None, old=None):
+        """solvers/ns2d/solver.py:111-194; compute_Frot :34-38."""
+        oper = self.oper
+        if state_spect is None:
+            rot_fft = self.state_spect.get_var("rot_fft")
+            ux = self.state_phys.get_var("ux")
+            uy = self.state_phys.get_var("uy")
+        else:
+            rot_fft = state_spect.get_var("rot_fft")
+            ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
+            ux, uy = self.fields_tmp[0:2]
+            oper.ifft_as_arg(ux_fft, ux)
+            oper.ifft_as_arg(uy_fft, uy)
+        px_rot_fft, py_rot_fft = oper.gradfft_from_fft(rot_fft)
+        px_rot, py_rot = self.fields_tmp[2:4]
+        oper.ifft_as_arg(px_rot_fft, px_rot)
+        oper.ifft_as_arg(py_rot_fft, py_rot)
+        if self.beta == 0:
+            Frot = -ux * px_rot - uy * py_rot
+        else:
+            Frot = -ux * px_rot - uy * (py_rot + self.beta)
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state_spect)
+        else:
+            tendencies_fft = old
+        Frot_fft = tendencies_fft.get_var("rot_fft")
+        oper.fft_as_arg(Frot, Frot_fft)
+        self.dealiasing(Frot_fft)
+        return tendencies_fft
+
+    # ------------------------------------------------------------------ schemes
+    def _time_step_RK2(self):
+        """base/time_stepping/pseudo_spect.py:469-517."""
+        dt = self.deltat
+        diss, diss2 = self.exact, self.exact2
+        state_spect = self.state_spect
+        tendencies_0 = self.tendencies_nonlin()
+        state_spect_12 = self._state_spect_tmp
+        step_Euler(state_spect, dt / 2, tendencies_0, diss2, output=state_spect_12)
+        tendencies_12 = self.tendencies_nonlin(state_spect_12, old=tendencies_0)
+        step_like_RK2(state_spect, dt, tendencies_12, diss, diss2)
+
+    def _time_step_RK4(self):
+        """base/time_stepping/pseudo_spect.py:798-984."""
+        dt = self.deltat
+        diss, diss2 = self.exact, self.exact2
+        state_spect = self.state_spect
+        tendencies_0 = self.tendencies_nonlin()
+        state_spect_tmp1 = self._state_spect_tmp1
+        state_spect_tmp = step_Euler(state_spect, dt / 6, tendencies_0, diss, output=self._state_spect_tmp)
+        state_spect_12_approx1 = step_Euler(
+            state_spect, dt / 2, tendencies_0, diss2, output=state_spect_tmp1
+        )
+        tendencies_1 = self.tendencies_nonlin(state_spect_12_approx1, old=tendencies_0)
+        state_spect_12_approx2 = state_spect_tmp1
+        state_spect_tmp[:] += dt / 3 * diss2 * tendencies_1  # :938
+        state_spect_12_approx2[:] = state_spect * diss2 + dt / 2 * tendencies_1  # :939-941
+        tendencies_2 = self.tendencies_nonlin(state_spect_12_approx2, old=tendencies_1)
+        state_spect_1_approx = state_spect_tmp1
+        state_spect_tmp[:] += dt / 3 * diss2 * tendencies_2  # :968
+        state_spect_1_approx[:] = state_spect * diss + dt * diss2 * tendencies_2  # :969-971
+        tendencies_3 = self.tendencies_nonlin(state_spect_1_approx, old=tendencies_2)
+        state_spect[:] = state_spect_tmp + dt / 6 * tendencies_3  # :984
+
+    def one_time_step(self):
+        """ns3d/time_stepping.py:8-20 (3-D) / pseudo_spect.py:236-243 (2-D) + base.py:243-244."""
+        if self.scheme == "RK4":
+            self._time_step_RK4()
+        elif self.scheme == "RK2":
+            self._time_step_RK2()
+        else:
+            raise ValueError(f'Problem name time_scheme ("{self.scheme}")')
+        if self.ndim == 3:
+            self.project_state_spect(self.state_spect)
+        self.dealiasing(self.state_spect)
+        self.statephys_from_statespect()
+        if np.isnan(np.sum(self.state_spect[0])):
+            raise ValueError(f"nan at it = {self.it}, t = {self.t:.4f}")
+        self.t += self.deltat
+        self.it += 1
+        return self.state_spect
+
+    # ------------------------------------------------------------------ CFL (base.py:320-354)
+    def compute_time_increment_CFL(self, cfl=1.0, deltat_max=0.2):
+        """base/time_stepping/base.py:320-354 (RK4: CFL = 1.0, :259-260)."""
+        oper = self.oper
+        if self.ndim == 3:
+            vx, vy, vz = (self.state_phys.get_var(k) for k in ("vx", "vy", "vz"))
+            freq = (
+                np.abs(vx).max() / oper.deltax
+                + np.abs(vy).max() / oper.deltay
+                + np.abs(vz).max() / oper.deltaz
+            )
+        else:
+            ux, uy = self.state_phys.get_var("ux"), self.state_phys.get_var("uy")
+            freq = np.abs(ux).max() / oper.deltax + np.abs(uy).max() / oper.deltay
+        deltat_CFL = cfl / freq if freq > 0 else deltat_max
+        deltat_wanted = min(deltat_CFL, deltat_max)
+        if abs(self.deltat - deltat_wanted) / deltat_wanted > 0.02:  # base.py:350-354
+            self.set_deltat(deltat_wanted)
+        return self.deltat
+
+    # ------------------------------------------------------------------ observables
+    def compute_energy(self):
+        """ns3d/output/__init__.py:101-117 ; ns2d energy = sum' |rot|^2/K2 / 2."""
+        oper = self.oper
+        if self.ndim == 3:
+            e = 0.0
+            for k in ("vx_fft", "vy_fft", "vz_fft"):
+                e += oper.sum_wavenumbers(0.5 * np.abs(self.state_spect.get_var(k)) ** 2)
+            return e
+        rot_fft = self.state_spect.get_var("rot_fft")
+        return oper.sum_wavenumbers(0.5 * np.abs(rot_fft) ** 2 / oper.K2_not0)
+
+    def compute_enstrophy(self):
+        oper = self.oper
+        if self.ndim == 2:
+            return oper.sum_wavenumbers(0.5 * np.abs(self.state_spect.get_var("rot_fft")) ** 2)
+        ox, oy, oz = oper.rotfft_from_vecfft(*(self.state_spect.get_var(k) for k in ("vx_fft", "vy_fft", "vz_fft")))
+        return oper.sum_wavenumbers(0.5 * (np.abs(ox) ** 2 + np.abs(oy) ** 2 + np.abs(oz) ** 2))
+
+    def compute_spectrum3d(self):
+        e = sum(
+            0.5 * np.abs(self.state_spect.get_var(k)) ** 2 for k in ("vx_fft", "vy_fft", "vz_fft")
+        )
+        return self.oper.compute_3dspectrum(e)
+
+    # ------------------------------------------------------------------ initial fields
+    def init_noise(self, velo_max=1.0, length=None, seed=42):
+        """ns3d/init_fields.py:110-196 ; ns2d/init_fields.py:57-108."""
+        oper = self.oper
+
+        def H_smooth(x, delta):
+            return (1.0 + np.tanh(2 * pi * x / delta)) / 2.0
+
+        if self.ndim == 3:
+            lambda0 = oper.Lx / 4.0 if length is None else length
+            np.random.seed(seed)
+            vv = [np.random.random(oper.shapeX_loc) - 0.5 for _ in range(3)]
+            vv_fft = []
+            for vi in vv:
+                vi_fft = oper.fft(vi)
+                vi_fft[0, 0, 0] = 0.0
+                vv_fft.append(vi_fft)
+            oper.project_perpk3d(*vv_fft)
+            for vi_fft in vv_fft:
+                self.dealiasing(vi_fft)
+            k0 = 2 * pi / lambda0
+            delta_k0 = 1.0 * k0
+            K = np.sqrt(oper.K2)
+            vv_fft = [vi_fft * H_smooth(k0 - K, delta_k0) for vi_fft in vv_fft]
+            vv = [oper.ifft(ui_fft) for ui_fft in vv_fft]
+            vmax = np.sqrt(vv[0] ** 2 + vv[1] ** 2 + vv[2] ** 2).max()
+            vv = [velo_max * vi / vmax for vi in vv]
+            fields = [oper.fft(vi) for vi in vv]
+            if self.solver == "ns3d.strat":
+                lambda0 = min(oper.Lx, oper.Ly, oper.Lz) / 4.0 if length is None else length
+                k0 = 2 * pi / lambda0
+                field = np.random.random(oper.shapeX_loc)
+                field_fft = oper.fft(field)
+                field_fft[0, 0, 0] = 0.0
+                field_fft *= H_smooth(k0 - K, 1.0 * k0)
+                oper.ifft_as_arg(field_fft, field)
+                value_max = np.abs(field).max()
+                fields.append((velo_max * self.N / value_max) * field_fft)
+            self.set_state_spect(np.stack(fields))
+        else:
+            lambda0 = min(oper.lx, oper.ly) / 4.0 if length is None else length
+            np.random.seed(seed)
+            shape = oper.shapeK_loc
+            ux_fft = np.random.random(shape) + 1j * np.random.random(shape) - 0.5 - 0.5j
+            uy_fft = np.random.random(shape) + 1j * np.random.random(shape) - 0.5 - 0.5j
+            ux_fft[0, 0] = 0.0
+            uy_fft[0, 0] = 0.0
+            oper.projection_perp(ux_fft, uy_fft)
+            oper.dealiasing_variable(ux_fft)
+            oper.dealiasing_variable(uy_fft)
+            k0 = 2 * pi / lambda0
+            ux_fft = ux_fft * H_smooth(k0 - oper.K, 1.0 * k0)
+            uy_fft = uy_fft * H_smooth(k0 - oper.K, 1.0 * k0)
+            ux = oper.ifft(ux_fft)
+            uy = oper.ifft(uy_fft)
+            vmax = np.sqrt(ux**2 + uy**2).max()
+            ux = velo_max * ux / vmax
+            uy = velo_max * uy / vmax
+            rot_fft = oper.rotfft_from_vecfft(oper.fft(ux), oper.fft(uy))
+            self.set_state_spect(rot_fft[None])
+
+    def init_taylor_green(self):
+        """doc/test_cases/Taylor_Green_vortices/run_simul.py:40-54."""
+        oper = self.oper
+        Z, Y, X = np.meshgrid(oper.z, oper.y, oper.x, indexing="ij")
+        vx = np.sin(X) * np.cos(Y) * np.cos(Z)
+        vy = -np.cos(X) * np.sin(Y) * np.cos(Z)
+        vz = np.zeros_like(vx)
+        self.set_state_spect(np.stack([oper.fft(v) for v in (vx, vy, vz)]))
