@@ -1,0 +1,841 @@
+// C ABI of libb200spectral.so: plan management, transforms, k-space / x-space operator kernels,
+// the fused tendencies_nonlin and the RK2 / RK4 time step.  See include/b200spectral.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "internal.h"
+
+// ------------------------------------------------------------------------------- errors / counters
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+int b2i_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return -1;
+}
+int b2i_check_launch(const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return b2i_set_error("%s: %s", what, cudaGetErrorString(e));
+    }
+    return 0;
+}
+void b2i_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+extern "C" const char* b2_last_error(void) { return g_err; }
+extern "C" int b2_version(void) { return 100; }
+extern "C" long long b2_launch_count(void) { return g_launches.load(); }
+
+#define CUDA_TRY(expr)                                                              \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) return b2i_set_error(#expr ": %s", cudaGetErrorString(_e)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------- plan
+static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+static int upload_twiddles(int n, cplx** out) {
+    std::vector<cplx> h(n > 0 ? n : 1);
+    const long double tau = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < n; ++k) {
+        long double a = tau * (long double)k / (long double)n;
+        h[k] = make_double2((double)cosl(a), (double)-sinl(a));
+    }
+    CUDA_TRY(cudaMalloc((void**)out, sizeof(cplx) * h.size()));
+    CUDA_TRY(cudaMemcpy(*out, h.data(), sizeof(cplx) * h.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** out) {
+    // fluidfft k_adim ordering: [0..n/2, -n/2+1..-1] (np.fft.fftfreq*n with +n/2 for even n)
+    std::vector<double> h(nkeep > 0 ? nkeep : 1, 0.0);
+    const double dk = L > 0 ? 2.0 * M_PI / L : 0.0;
+    for (int i = 0; i < nkeep; ++i) {
+        int k = i;
+        if (!half && i > n / 2) k = i - n;
+        h[i] = dk * (double)k;
+    }
+    CUDA_TRY(cudaMalloc((void**)out, sizeof(double) * h.size()));
+    CUDA_TRY(cudaMemcpy(*out, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int b2_plan_create(b2_plan** out, int ndim, int n0, int n1, int n2, double L0, double L1,
+                              double L2) {
+    if (!out) return b2i_set_error("b2_plan_create: out is NULL");
+    if (ndim != 2 && ndim != 3) return b2i_set_error("b2_plan_create: ndim must be 2 or 3");
+    b2_plan* p = new b2_plan();
+    memset(p, 0, sizeof(*p));
+    p->ndim = ndim;
+    if (ndim == 2) {
+        p->n0 = 1; p->n1 = n0; p->n2 = n1;
+        p->L0 = 0.0; p->L1 = L0; p->L2 = L1;
+    } else {
+        p->n0 = n0; p->n1 = n1; p->n2 = n2;
+        p->L0 = L0; p->L1 = L1; p->L2 = L2;
+    }
+    if (p->n0 < 1 || p->n1 < 1 || p->n2 < 2) {
+        delete p;
+        return b2i_set_error("b2_plan_create: bad shape (%d, %d, %d)", n0, n1, n2);
+    }
+    p->nk = p->n2 / 2 + 1;
+    p->fast0 = is_pow2(p->n0) && p->n0 >= 8 && p->n0 <= 2048;
+    p->fast1 = is_pow2(p->n1) && p->n1 >= 8 && p->n1 <= 2048;
+    p->fast2 = is_pow2(p->n2) && p->n2 >= 8 && p->n2 <= 2048;
+    int e = 0;
+    e |= upload_twiddles(p->n0, &p->tw0);
+    e |= upload_twiddles(p->n1, &p->tw1);
+    e |= upload_twiddles(p->n2, &p->tw2);
+    e |= upload_wavenumbers(p->n0, p->n0, p->L0, false, &p->k0);
+    e |= upload_wavenumbers(p->n1, p->n1, p->L1, false, &p->k1);
+    e |= upload_wavenumbers(p->n2, p->nk, p->L2, true, &p->kx);
+    if (e) {
+        b2_plan_destroy(p);
+        return -1;
+    }
+    p->solver = -1;
+    *out = p;
+    return 0;
+}
+
+extern "C" int b2_plan_destroy(b2_plan* p) {
+    if (!p) return 0;
+    cudaFree(p->tw0); cudaFree(p->tw1); cudaFree(p->tw2);
+    cudaFree(p->k0); cudaFree(p->k1); cudaFree(p->kx);
+    delete p;
+    return 0;
+}
+
+extern "C" int b2_plan_shapes(const b2_plan* p, int* shapeX, int* shapeK) {
+    shapeX[0] = p->n0; shapeX[1] = p->n1; shapeX[2] = p->n2;
+    shapeK[0] = p->n0; shapeK[1] = p->n1; shapeK[2] = p->nk;
+    return 0;
+}
+
+extern "C" int b2_plan_is_fast(const b2_plan* p) {
+    return (p->n0 == 1 || p->fast0) && p->fast1 && p->fast2;
+}
+
+// ------------------------------------------------------------------------------- transforms
+extern "C" int b2_fft_r2c(b2_plan* p, const double* X, double* K, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    cplx* k = reinterpret_cast<cplx*>(K);
+    const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
+    int e = b2i_xpass_r2c(p, X, k, scale, s);
+    if (e) return e;
+    const cplx* in[1] = {k};
+    cplx* out[1] = {k};
+    if ((e = b2i_strided_plain(p, 1, -1, in, out, 1, 1.0, s))) return e;
+    return b2i_strided_plain(p, 0, -1, in, out, 1, 1.0, s);
+}
+
+extern "C" int b2_ifft_c2r(b2_plan* p, const double* K, double* X, double* work, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const cplx* k = reinterpret_cast<const cplx*>(K);
+    cplx* w = work ? reinterpret_cast<cplx*>(work) : const_cast<cplx*>(k);
+    const cplx* in[1] = {k};
+    cplx* out[1] = {w};
+    const cplx* inw[1] = {w};
+    int e;
+    if (p->n0 > 1) {
+        if ((e = b2i_strided_plain(p, 0, +1, in, out, 1, 1.0, s))) return e;
+        if ((e = b2i_strided_plain(p, 1, +1, inw, out, 1, 1.0, s))) return e;
+    } else {
+        if ((e = b2i_strided_plain(p, 1, +1, in, out, 1, 1.0, s))) return e;
+    }
+    return b2i_xpass_c2r(p, w, X, s);
+}
+
+// ------------------------------------------------------------------------------- pointwise kernels
+// One CTA per (i0, i1) row, threads run over kx: wavenumbers along axes 0 / 1 are per-block
+// constants, accesses are coalesced 16-byte elements.
+struct KGrid {
+    const double *k0, *k1, *kx;
+    int n0, n1, nk;
+};
+static KGrid kgrid(const b2_plan* p) { return KGrid{p->k0, p->k1, p->kx, p->n0, p->n1, p->nk}; }
+#define B2_ROW_SETUP                                         \
+    const long long row = blockIdx.x;                        \
+    const int i0 = (int)(row / g.n1);                        \
+    const int i1 = (int)(row - (long long)i0 * g.n1);        \
+    const double Kz = g.k0[i0], Ky = g.k1[i1];               \
+    const long long rbase = row * g.nk;
+static inline unsigned nrows(const b2_plan* p) { return (unsigned)((long long)p->n0 * p->n1); }
+#define B2_ROW_THREADS 128
+
+__global__ void rot_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* vz, cplx* rx, cplx* ry,
+                           cplx* rz) {
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        const cplx a = vx[i], b = vy[i], c = vz[i];
+        rx[i] = make_double2(-(Ky * c.y - Kz * b.y), Ky * c.x - Kz * b.x);
+        ry[i] = make_double2(-(Kz * a.y - Kx * c.y), Kz * a.x - Kx * c.x);
+        rz[i] = make_double2(-(Kx * b.y - Ky * a.y), Kx * b.x - Ky * a.x);
+    }
+}
+
+__global__ void div_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* vz, cplx* d) {
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        const cplx a = vx[i], b = vy[i], c = vz[i];
+        const double tr = Kx * a.x + Ky * b.x + Kz * c.x;
+        const double ti = Kx * a.y + Ky * b.y + Kz * c.y;
+        d[i] = make_double2(-ti, tr);
+    }
+}
+
+B2_DEVINL double inv_k2_nozero(double K2, bool is_origin) { return 1.0 / (is_origin ? 1e-14 : K2); }
+
+B2_DEVINL void project3(double Kx, double Ky, double Kz, double invK2, cplx& a, cplx& b, cplx& c) {
+    // project_perpk3d: tmp = (Kx vx + Ky vy + Kz vz) * inv_K_square_nozero ; v -= K tmp
+    const double tr = (Kx * a.x + Ky * b.x + Kz * c.x) * invK2;
+    const double ti = (Kx * a.y + Ky * b.y + Kz * c.y) * invK2;
+    a.x -= Kx * tr; a.y -= Kx * ti;
+    b.x -= Ky * tr; b.y -= Ky * ti;
+    c.x -= Kz * tr; c.y -= Kz * ti;
+}
+
+__global__ void project_kernel(KGrid g, cplx* vx, cplx* vy, cplx* vz) {
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        cplx a = vx[i], b = vy[i], c = vz[i];
+        const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
+        project3(Kx, Ky, Kz, inv_k2_nozero(K2, row == 0 && ikx == 0), a, b, c);
+        vx[i] = a; vy[i] = b; vz[i] = c;
+    }
+}
+
+__global__ void dealias_kernel(cplx* f, long long fsize, int nvar, const uint8_t* mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fsize) return;
+    if (mask[i]) {
+        for (int v = 0; v < nvar; ++v) f[v * fsize + i] = make_double2(0.0, 0.0);
+    }
+}
+
+__global__ void vecprod_kernel(const double* ax, const double* ay, const double* az, double* bx,
+                               double* by, double* bz, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a0 = ax[i], a1 = ay[i], a2 = az[i], b0 = bx[i], b1 = by[i], b2 = bz[i];
+    bx[i] = a1 * b2 - a2 * b1;
+    by[i] = a2 * b0 - a0 * b2;
+    bz[i] = a0 * b1 - a1 * b0;
+}
+
+__global__ void mul_real_kernel(const double* a, const double* b, double* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] * b[i];
+}
+
+__global__ void frot_kernel(const double* ux, const double* uy, const double* px, const double* py,
+                            double beta, double* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    o[i] = beta == 0.0 ? -ux[i] * px[i] - uy[i] * py[i] : -ux[i] * px[i] - uy[i] * (py[i] + beta);
+}
+
+__global__ void fb_kernel(cplx* d, double N2, const cplx* vz, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const cplx a = d[i], b = vz[i];
+    d[i] = make_double2(-a.x - N2 * b.x, -a.y - N2 * b.y);
+}
+
+__global__ void add_kernel(cplx* a, const cplx* b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cplx x = a[i];
+    const cplx y = b[i];
+    x.x += y.x; x.y += y.y;
+    a[i] = x;
+}
+
+// 2-D operators (plans stored with n0 == 1: Ky = k1, Kx = kx)
+__global__ void vec_from_rot2d_kernel(KGrid g, const cplx* rot, cplx* ux, cplx* uy) {
+    B2_ROW_SETUP
+    (void)Kz;
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        double K2 = Kx * Kx + Ky * Ky;
+        if (row == 0 && ikx == 0) K2 = 1e-14;
+        const double inv = 1.0 / K2;
+        const cplx r = rot[i];
+        const double cy = Ky * inv, cx = Kx * inv;
+        ux[i] = make_double2(-cy * r.y, cy * r.x);
+        uy[i] = make_double2(cx * r.y, -(cx * r.x));
+    }
+}
+__global__ void grad2d_kernel(KGrid g, const cplx* f, cplx* px, cplx* py) {
+    B2_ROW_SETUP
+    (void)Kz;
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        const cplx r = f[i];
+        px[i] = make_double2(-Kx * r.y, Kx * r.x);
+        py[i] = make_double2(-Ky * r.y, Ky * r.x);
+    }
+}
+__global__ void rot2d_kernel(KGrid g, const cplx* ux, const cplx* uy, cplx* rot) {
+    B2_ROW_SETUP
+    (void)Kz;
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        const cplx a = ux[i], b = uy[i];
+        rot[i] = make_double2(-(Kx * b.y - Ky * a.y), Kx * b.x - Ky * a.x);
+    }
+}
+
+#define B2_1D_GRID(n) (unsigned)(((n) + 255) / 256), 256
+
+extern "C" int b2_rotfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const double* vz,
+                                     double* rx, double* ry, double* rz, void* stream) {
+    rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        kgrid(p), (const cplx*)vx, (const cplx*)vy, (const cplx*)vz, (cplx*)rx, (cplx*)ry, (cplx*)rz);
+    B2_LAUNCH_CHECK("rot_kernel");
+    return 0;
+}
+extern "C" int b2_divfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const double* vz,
+                                     double* d, void* stream) {
+    div_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        kgrid(p), (const cplx*)vx, (const cplx*)vy, (const cplx*)vz, (cplx*)d);
+    B2_LAUNCH_CHECK("div_kernel");
+    return 0;
+}
+extern "C" int b2_project_perpk3d(b2_plan* p, double* vx, double* vy, double* vz, void* stream) {
+    project_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (cplx*)vx, (cplx*)vy,
+                                                                           (cplx*)vz);
+    B2_LAUNCH_CHECK("project_kernel");
+    return 0;
+}
+extern "C" int b2_vector_product(const double* ax, const double* ay, const double* az, double* bx,
+                                 double* by, double* bz, long long n, void* stream) {
+    vecprod_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(ax, ay, az, bx, by, bz, n);
+    B2_LAUNCH_CHECK("vecprod_kernel");
+    return 0;
+}
+extern "C" int b2_mul_real(const double* a, const double* b, double* out, long long n, void* stream) {
+    mul_real_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(a, b, out, n);
+    B2_LAUNCH_CHECK("mul_real_kernel");
+    return 0;
+}
+extern "C" int b2_dealias(b2_plan* p, double* fields, int nvar, const uint8_t* mask, void* stream) {
+    const long long n = p->fsize();
+    dealias_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>((cplx*)fields, n, nvar, mask);
+    B2_LAUNCH_CHECK("dealias_kernel");
+    return 0;
+}
+extern "C" int b2_vecfft_from_rotfft2d(b2_plan* p, const double* rot, double* ux, double* uy,
+                                       void* stream) {
+    vec_from_rot2d_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        kgrid(p), (const cplx*)rot, (cplx*)ux, (cplx*)uy);
+    B2_LAUNCH_CHECK("vec_from_rot2d_kernel");
+    return 0;
+}
+extern "C" int b2_gradfft_from_fft2d(b2_plan* p, const double* f, double* px, double* py, void* stream) {
+    grad2d_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (const cplx*)f,
+                                                                          (cplx*)px, (cplx*)py);
+    B2_LAUNCH_CHECK("grad2d_kernel");
+    return 0;
+}
+extern "C" int b2_rotfft_from_vecfft2d(b2_plan* p, const double* ux, const double* uy, double* rot,
+                                       void* stream) {
+    rot2d_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (const cplx*)ux,
+                                                                         (const cplx*)uy, (cplx*)rot);
+    B2_LAUNCH_CHECK("rot2d_kernel");
+    return 0;
+}
+extern "C" int b2_compute_frot(const double* ux, const double* uy, const double* px, const double* py,
+                               double beta, double* out, long long n, void* stream) {
+    frot_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(ux, uy, px, py, beta, out, n);
+    B2_LAUNCH_CHECK("frot_kernel");
+    return 0;
+}
+extern "C" int b2_compute_fb_fft(double* div_vb, double N, const double* vz, long long nk, void* stream) {
+    fb_kernel<<<B2_1D_GRID(nk), 0, (cudaStream_t)stream>>>((cplx*)div_vb, N * N, (const cplx*)vz, nk);
+    B2_LAUNCH_CHECK("fb_kernel");
+    return 0;
+}
+extern "C" int b2_add_inplace(double* a, const double* b, long long nk, void* stream) {
+    add_kernel<<<B2_1D_GRID(nk), 0, (cudaStream_t)stream>>>((cplx*)a, (const cplx*)b, nk);
+    B2_LAUNCH_CHECK("add_kernel");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- linear term
+struct Visc {
+    double nu2, nu4, nu8, num4;
+    double k2_hypo_origin;  // K2 at index [0,0,1] (2-D: [0,1]) used to patch the K=0 mode
+};
+static Visc visc_of(const b2_plan* p, double nu2, double nu4, double nu8, double num4) {
+    const double dkx = 2.0 * M_PI / p->L2;
+    return Visc{nu2, nu4, nu8, num4, dkx * dkx};
+}
+// compute_freq_diss, /root/reference/fluidsim/base/solvers/pseudo_spect.py:161-189
+B2_DEVINL double freq_diss(const Visc& v, double K2, bool is_origin) {
+    double fd = v.nu2 > 0.0 ? v.nu2 * K2 : 0.0;
+    const double K4 = K2 * K2;
+    if (v.nu4 > 0.0) fd += v.nu4 * K4;
+    if (v.nu8 > 0.0) fd += v.nu8 * (K4 * K4);
+    if (v.num4 != 0.0) {
+        const double k2n = is_origin ? v.k2_hypo_origin : K2;
+        fd += v.num4 / (k2n * k2n);
+    }
+    return fd;
+}
+
+__global__ void exact_coefs_kernel(KGrid g, Visc v, double dt, double* exact, double* exact2) {
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
+        const double fd = freq_diss(v, K2, row == 0 && ikx == 0);
+        exact[rbase + ikx] = exp(-dt * fd);
+        exact2[rbase + ikx] = exp(-dt / 2 * fd);
+    }
+}
+extern "C" int b2_exact_coefs(b2_plan* p, double nu2, double nu4, double nu8, double num4, double dt,
+                              double* exact, double* exact2, void* stream) {
+    exact_coefs_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(
+        kgrid(p), visc_of(p, nu2, nu4, nu8, num4), dt, exact, exact2);
+    B2_LAUNCH_CHECK("exact_coefs_kernel");
+    return 0;
+}
+
+// elementwise RK kernels with explicit diss arrays (operator-level API)
+template <int MODE>
+__global__ void rk_elem_kernel(long long fsize, int nvar, cplx* S, cplx* acc, cplx* O, const cplx* T,
+                               const double* diss, const double* diss2, double dt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fsize) return;
+    const double d1 = diss ? diss[i] : 1.0, d2 = diss2 ? diss2[i] : 1.0;
+    for (int v = 0; v < nvar; ++v) {
+        const long long j = v * fsize + i;
+        const cplx t = T[j];
+        if (MODE == 0) {  // step_Euler: O = (S + dt T) diss
+            const cplx s = S[j];
+            O[j] = make_double2((s.x + dt * t.x) * d1, (s.y + dt * t.y) * d1);
+        } else if (MODE == 1) {  // step_like_RK2: S = S diss + dt diss2 T
+            const cplx s = S[j];
+            const double c = dt * d2;
+            S[j] = make_double2(s.x * d1 + c * t.x, s.y * d1 + c * t.y);
+        } else if (MODE == 2) {  // rk4_step1: acc += dt/3 diss2 T ; O = S diss2 + dt/2 T
+            const cplx s = S[j];
+            cplx a = acc[j];
+            const double c = dt / 3 * d2;
+            a.x += c * t.x; a.y += c * t.y;
+            acc[j] = a;
+            const double h = dt / 2;
+            O[j] = make_double2(s.x * d2 + h * t.x, s.y * d2 + h * t.y);
+        } else if (MODE == 3) {  // rk4_step2: acc += dt/3 diss2 T ; O = S diss + dt diss2 T
+            const cplx s = S[j];
+            cplx a = acc[j];
+            const double c = dt / 3 * d2;
+            a.x += c * t.x; a.y += c * t.y;
+            acc[j] = a;
+            const double c2 = dt * d2;
+            O[j] = make_double2(s.x * d1 + c2 * t.x, s.y * d1 + c2 * t.y);
+        } else {  // rk4_step3: S = acc + dt/6 T
+            const cplx a = acc[j];
+            const double c = dt / 6;
+            S[j] = make_double2(a.x + c * t.x, a.y + c * t.y);
+        }
+    }
+}
+
+extern "C" int b2_step_euler(b2_plan* p, const double* S, double dt, const double* T, const double* diss,
+                             double* out, int nvar, void* stream) {
+    const long long n = p->fsize();
+    rk_elem_kernel<0><<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(n, nvar, (cplx*)S, nullptr, (cplx*)out,
+                                                                  (const cplx*)T, diss, nullptr, dt);
+    B2_LAUNCH_CHECK("rk_elem_kernel<0>");
+    return 0;
+}
+extern "C" int b2_step_like_rk2(b2_plan* p, double* S, double dt, const double* T, const double* diss,
+                                const double* diss2, int nvar, void* stream) {
+    const long long n = p->fsize();
+    rk_elem_kernel<1><<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(n, nvar, (cplx*)S, nullptr, nullptr,
+                                                                  (const cplx*)T, diss, diss2, dt);
+    B2_LAUNCH_CHECK("rk_elem_kernel<1>");
+    return 0;
+}
+extern "C" int b2_rk4_step1(b2_plan* p, const double* S, double* acc, double* S12, const double* T,
+                            const double* diss2, double dt, int nvar, void* stream) {
+    const long long n = p->fsize();
+    rk_elem_kernel<2><<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(n, nvar, (cplx*)S, (cplx*)acc, (cplx*)S12,
+                                                                  (const cplx*)T, nullptr, diss2, dt);
+    B2_LAUNCH_CHECK("rk_elem_kernel<2>");
+    return 0;
+}
+extern "C" int b2_rk4_step2(b2_plan* p, const double* S, double* acc, double* S1, const double* T,
+                            const double* diss, const double* diss2, double dt, int nvar, void* stream) {
+    const long long n = p->fsize();
+    rk_elem_kernel<3><<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(n, nvar, (cplx*)S, (cplx*)acc, (cplx*)S1,
+                                                                  (const cplx*)T, diss, diss2, dt);
+    B2_LAUNCH_CHECK("rk_elem_kernel<3>");
+    return 0;
+}
+extern "C" int b2_rk4_step3(b2_plan* p, double* S, const double* acc, const double* T, double dt, int nvar,
+                            void* stream) {
+    const long long n = p->fsize();
+    rk_elem_kernel<4><<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(n, nvar, (cplx*)S, (cplx*)acc, nullptr,
+                                                                  (const cplx*)T, nullptr, nullptr, dt);
+    B2_LAUNCH_CHECK("rk_elem_kernel<4>");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- reductions
+B2_DEVINL double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+B2_DEVINL double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+B2_DEVINL void atomic_max_double(double* addr, double v) {  // v >= 0
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// sum_wavenumbers(|f|^2): weight 1 for kx=0 and (even nx) kx=nx/2, else 2
+__global__ void sumk_abs2_kernel(KGrid g, const cplx* f, long long fsize, int nvar, int nx_even,
+                                 double* out) {
+    __shared__ double sh[B2_ROW_THREADS / 32];
+    const long long rbase = (long long)blockIdx.x * g.nk;
+    double acc = 0.0;
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double w = (ikx == 0 || (nx_even && ikx == g.nk - 1)) ? 1.0 : 2.0;
+        double e = 0.0;
+        for (int v = 0; v < nvar; ++v) {
+            const cplx a = f[v * fsize + rbase + ikx];
+            e += a.x * a.x + a.y * a.y;
+        }
+        acc += w * e;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < B2_ROW_THREADS / 32; ++i) t += sh[i];
+        atomicAdd(out, t);
+    }
+}
+extern "C" int b2_sum_wavenumbers_abs2(b2_plan* p, const double* fields, int nvar, double* out_dev,
+                                       void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+    sumk_abs2_kernel<<<nrows(p), B2_ROW_THREADS, 0, s>>>(kgrid(p), (const cplx*)fields, p->fsize(), nvar,
+                                                         p->n2 % 2 == 0, out_dev);
+    B2_LAUNCH_CHECK("sumk_abs2_kernel");
+    return 0;
+}
+
+template <int OP>  // 0: max |x| ; 1: sum
+__global__ void reduce_kernel(const double* x, long long n, double* out) {
+    __shared__ double sh[8];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        if (OP == 0) {
+            // NaN-propagating max so that a blown-up field is visible
+            acc = (v != v) ? v : fmax(acc, fabs(v));
+        } else {
+            acc += v;
+        }
+    }
+    acc = OP == 0 ? warp_max(acc) : warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = sh[0];
+        for (int i = 1; i < 8; ++i) t = OP == 0 ? fmax(t, sh[i]) : t + sh[i];
+        if (OP == 0) atomic_max_double(out, t);
+        else atomicAdd(out, t);
+    }
+}
+extern "C" int b2_max_abs(const double* x, long long n, double* out_dev, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+    const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    reduce_kernel<0><<<grid ? grid : 1, 256, 0, s>>>(x, n, out_dev);
+    B2_LAUNCH_CHECK("reduce_kernel<max>");
+    return 0;
+}
+extern "C" int b2_sum(const double* x, long long n, double* out_dev, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+    const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    reduce_kernel<1><<<grid ? grid : 1, 256, 0, s>>>(x, n, out_dev);
+    B2_LAUNCH_CHECK("reduce_kernel<sum>");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- fused path
+extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4,
+                              int has_f, double f, double N, double beta, const uint8_t* mask) {
+    if (solver < 0 || solver > 2) return b2i_set_error("b2_set_physics: unknown solver %d", solver);
+    if ((solver == B2_SOLVER_NS2D) != (p->ndim == 2))
+        return b2i_set_error("b2_set_physics: solver %d does not match a %d-D plan", solver, p->ndim);
+    p->solver = solver;
+    p->nu2 = nu2; p->nu4 = nu4; p->nu8 = nu8; p->num4 = num4;
+    p->has_f = has_f; p->f = f; p->N = N; p->beta = beta;
+    p->mask = mask;
+    return 0;
+}
+
+extern "C" int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar) {
+    (void)p;
+    switch (solver) {
+        case B2_SOLVER_NS3D: *nwork = 6; *nvar = 3; return 0;
+        case B2_SOLVER_NS3D_STRAT: *nwork = 7; *nvar = 4; return 0;
+        case B2_SOLVER_NS2D: *nwork = 4; *nvar = 1; return 0;
+    }
+    return b2i_set_error("b2_work_fields: unknown solver %d", solver);
+}
+
+extern "C" int b2_set_buffers(b2_plan* p, double* acc, double* stage, double* work) {
+    p->acc = (cplx*)acc; p->stage = (cplx*)stage; p->work = (cplx*)work;
+    return 0;
+}
+
+enum { M_TEND = 0, M_RK4_0, M_RK4_1, M_RK4_2, M_RK4_3, M_RK2_0, M_RK2_1 };
+
+struct RKArgs {
+    KGrid g;
+    Visc visc;
+    const cplx* W;    // raw FFT output: nwork_out fields, stride fsize
+    const cplx* Sin;  // stage input (strat coupling terms)
+    cplx* S;          // state (nvar fields)
+    cplx* A;          // accumulator
+    cplx* B;          // next stage input
+    cplx* Tout;       // M_TEND output
+    const uint8_t* mask;
+    long long fsize;
+    double dt, N2;
+};
+
+// Epilogue of a stage: raw FFT(v x omega) -> (+ buoyancy terms) -> Leray projection -> dealiasing
+// -> exact-linear RK update.  Replaces project_state_spect + oper.dealiasing
+// (/root/reference/fluidsim/solvers/ns3d/solver.py:251-263), compute_fb_fft
+// (strat/solver.py:29-33, 198, 206-209) and step_Euler / rk4_step1-3 / step_like_RK2
+// (base/time_stepping/pseudo_spect.py:51-68, 902-984, 503-517).
+template <int SOLVER, int MODE>
+__global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
+    constexpr int NV = SOLVER == B2_SOLVER_NS3D ? 3 : (SOLVER == B2_SOLVER_NS3D_STRAT ? 4 : 1);
+    const KGrid& g = a.g;
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        const bool origin = row == 0 && ikx == 0;
+        const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
+        const double invK2 = inv_k2_nozero(K2, origin);
+        const bool masked = a.mask ? a.mask[i] != 0 : false;
+        cplx T[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) T[v] = a.W[v * a.fsize + i];
+        if (SOLVER == B2_SOLVER_NS3D_STRAT) {
+            const cplx b = a.Sin[3 * a.fsize + i], vz = a.Sin[2 * a.fsize + i];
+            T[2].x += b.x; T[2].y += b.y;
+            const cplx w3 = a.W[3 * a.fsize + i], w4 = a.W[4 * a.fsize + i], w5 = a.W[5 * a.fsize + i];
+            const double dr = Kx * w3.x + Ky * w4.x + Kz * w5.x;
+            const double di = Kx * w3.y + Ky * w4.y + Kz * w5.y;
+            // div = i (dr + i di) = (-di, dr);  fb = -div - N^2 vz
+            T[3] = make_double2(di - a.N2 * vz.x, -dr - a.N2 * vz.y);
+        }
+        if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, T[0], T[1], T[2]);
+        if (masked) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) T[v] = make_double2(0.0, 0.0);
+        }
+        if (MODE == M_TEND) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) a.Tout[v * a.fsize + i] = T[v];
+            continue;
+        }
+        const double dt = a.dt;
+        double E = 1.0, E2 = 1.0;
+        if (MODE != M_RK4_3) {
+            const double fd = freq_diss(a.visc, K2, origin);
+            if (MODE != M_RK4_1 && MODE != M_RK2_0) E = exp(-dt * fd);
+            if (MODE != M_RK4_3) E2 = exp(-dt / 2 * fd);
+        }
+        cplx Sn[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const long long j = v * a.fsize + i;
+            const cplx t = T[v];
+            if (MODE == M_RK4_0) {
+                const cplx s = a.S[j];
+                const double c6 = dt / 6, c2 = dt / 2;
+                a.A[j] = make_double2((s.x + c6 * t.x) * E, (s.y + c6 * t.y) * E);
+                a.B[j] = make_double2((s.x + c2 * t.x) * E2, (s.y + c2 * t.y) * E2);
+            } else if (MODE == M_RK4_1) {
+                const cplx s = a.S[j];
+                cplx ac = a.A[j];
+                const double c = dt / 3 * E2, h = dt / 2;
+                ac.x += c * t.x; ac.y += c * t.y;
+                a.A[j] = ac;
+                a.B[j] = make_double2(s.x * E2 + h * t.x, s.y * E2 + h * t.y);
+            } else if (MODE == M_RK4_2) {
+                const cplx s = a.S[j];
+                cplx ac = a.A[j];
+                const double c = dt / 3 * E2, c2 = dt * E2;
+                ac.x += c * t.x; ac.y += c * t.y;
+                a.A[j] = ac;
+                a.B[j] = make_double2(s.x * E + c2 * t.x, s.y * E + c2 * t.y);
+            } else if (MODE == M_RK4_3) {
+                const cplx ac = a.A[j];
+                const double c = dt / 6;
+                Sn[v] = make_double2(ac.x + c * t.x, ac.y + c * t.y);
+            } else if (MODE == M_RK2_0) {
+                const cplx s = a.S[j];
+                const double h = dt / 2;
+                a.B[j] = make_double2((s.x + h * t.x) * E2, (s.y + h * t.y) * E2);
+            } else {  // M_RK2_1
+                const cplx s = a.S[j];
+                const double c2 = dt * E2;
+                Sn[v] = make_double2(s.x * E + c2 * t.x, s.y * E + c2 * t.y);
+            }
+        }
+        if (MODE == M_RK4_3 || MODE == M_RK2_1) {
+            // end of step: project_state_spect + dealiasing (solvers/ns3d/time_stepping.py:15-16)
+            if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, Sn[0], Sn[1], Sn[2]);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                a.S[v * a.fsize + i] = masked ? make_double2(0.0, 0.0) : Sn[v];
+        }
+    }
+}
+
+template <int SOLVER>
+static int launch_rk_stage_s(int mode, const RKArgs& a, unsigned grid, cudaStream_t s) {
+    switch (mode) {
+#define B2_CASE(m) case m: rk_stage_kernel<SOLVER, m><<<grid, B2_ROW_THREADS, 0, s>>>(a); break;
+        B2_CASE(M_TEND) B2_CASE(M_RK4_0) B2_CASE(M_RK4_1) B2_CASE(M_RK4_2) B2_CASE(M_RK4_3)
+        B2_CASE(M_RK2_0) B2_CASE(M_RK2_1)
+#undef B2_CASE
+        default: return b2i_set_error("bad RK mode");
+    }
+    B2_LAUNCH_CHECK("rk_stage_kernel");
+    return 0;
+}
+
+static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s) {
+    const unsigned grid = nrows(p);
+    switch (p->solver) {
+        case B2_SOLVER_NS3D: return launch_rk_stage_s<B2_SOLVER_NS3D>(mode, a, grid, s);
+        case B2_SOLVER_NS3D_STRAT: return launch_rk_stage_s<B2_SOLVER_NS3D_STRAT>(mode, a, grid, s);
+        case B2_SOLVER_NS2D: return launch_rk_stage_s<B2_SOLVER_NS2D>(mode, a, grid, s);
+    }
+    return b2i_set_error("physics not set");
+}
+
+// raw nonlinear term of stage input `Sin` into work[0..nout-1] (scaled FFT, not yet projected)
+static int nonlinear_raw(b2_plan* p, const cplx* Sin, cudaStream_t s) {
+    int nwork, nvar;
+    if (b2_work_fields(p, p->solver, &nwork, &nvar)) return -1;
+    const long long fs = p->fsize();
+    const cplx* in[8];
+    cplx* W[8];
+    const cplx* Wc[8];
+    for (int v = 0; v < nvar; ++v) in[v] = Sin + v * fs;
+    for (int f = 0; f < nwork; ++f) Wc[f] = W[f] = p->work + f * fs;
+    const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
+    const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
+    int e;
+    if ((e = b2i_first_inverse_pass(p, in, W, s))) return e;
+    if (p->n0 > 1)
+        if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s))) return e;
+    if ((e = b2i_xpass_fused(p, W, scale, s))) return e;
+    if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s))) return e;
+    if ((e = b2i_strided_plain(p, 0, -1, Wc, W, nout, 1.0, s))) return e;
+    return 0;
+}
+
+static int check_fused_ready(b2_plan* p, bool need_rk) {
+    if (p->solver < 0) return b2i_set_error("b2_set_physics has not been called");
+    if (!b2_plan_is_fast(p))
+        return b2i_set_error("fused path needs power-of-two sizes in [8, 2048] (got %d x %d x %d)", p->n0,
+                             p->n1, p->n2);
+    if (!p->work) return b2i_set_error("b2_set_buffers has not been called (work)");
+    if (need_rk && (!p->acc || !p->stage)) return b2i_set_error("b2_set_buffers: acc/stage missing");
+    return 0;
+}
+
+static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
+    RKArgs a;
+    a.g = kgrid(p);
+    a.visc = visc_of(p, p->nu2, p->nu4, p->nu8, p->num4);
+    a.W = p->work;
+    a.Sin = Sin;
+    a.S = S;
+    a.A = p->acc;
+    a.B = p->stage;
+    a.Tout = nullptr;
+    a.mask = p->mask;
+    a.fsize = p->fsize();
+    a.dt = dt;
+    a.N2 = p->N * p->N;
+    return a;
+}
+
+extern "C" int b2_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = check_fused_ready(p, false))) return e;
+    const cplx* Sin = (const cplx*)S_in;
+    if ((e = nonlinear_raw(p, Sin, s))) return e;
+    RKArgs a = rk_args(p, Sin, nullptr, 0.0);
+    a.Tout = (cplx*)T_out;
+    return launch_rk_stage(p, M_TEND, a, s);
+}
+
+extern "C" int b2_time_step(b2_plan* p, int scheme, double dt, double* S_, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = check_fused_ready(p, true))) return e;
+    cplx* S = (cplx*)S_;
+    if (scheme == B2_SCHEME_RK4) {
+        const int modes[4] = {M_RK4_0, M_RK4_1, M_RK4_2, M_RK4_3};
+        for (int st = 0; st < 4; ++st) {
+            const cplx* Sin = st == 0 ? S : p->stage;
+            if ((e = nonlinear_raw(p, Sin, s))) return e;
+            RKArgs a = rk_args(p, Sin, S, dt);
+            if ((e = launch_rk_stage(p, modes[st], a, s))) return e;
+        }
+        return 0;
+    }
+    if (scheme == B2_SCHEME_RK2) {
+        const int modes[2] = {M_RK2_0, M_RK2_1};
+        for (int st = 0; st < 2; ++st) {
+            const cplx* Sin = st == 0 ? S : p->stage;
+            if ((e = nonlinear_raw(p, Sin, s))) return e;
+            RKArgs a = rk_args(p, Sin, S, dt);
+            if ((e = launch_rk_stage(p, modes[st], a, s))) return e;
+        }
+        return 0;
+    }
+    return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
+}

@@ -1,0 +1,222 @@
+// Register-resident Stockham FFT core for power-of-two line lengths (float64, sm_100a).
+//
+// One FFT line of N complex128 points is held by T = N/E threads, E points per thread
+// (thread t owns positions t + m*T).  Each stage is a radix-r butterfly done in registers
+// (r = E except possibly the last stage); between stages the line is re-distributed
+// through a padded shared-memory plane pair (re / im planes of doubles, so every access
+// is a conflict-free 64-bit access).  First-stage inputs and last-stage outputs sit at
+// positions t + m*T, i.e. loads and stores go straight between HBM and registers.
+//
+// Replaces: the FFTW plans behind fluidfft's fft_as_arg / ifft_as_arg
+// (/root/reference/fluidsim/solvers/ns3d/solver.py:210-241).
+#pragma once
+#include <cuda_runtime.h>
+
+typedef double2 cplx;
+
+#define B2_DEVINL __device__ __forceinline__
+
+B2_DEVINL cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+B2_DEVINL cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+B2_DEVINL cplx cmul(cplx a, cplx b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+B2_DEVINL cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+B2_DEVINL cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+// multiply by DIR*i  (DIR=-1: forward transform convention exp(-i..), DIR=+1: inverse)
+template <int DIR>
+B2_DEVINL cplx cmul_i(cplx a) {
+    return DIR < 0 ? make_double2(a.y, -a.x) : make_double2(-a.y, a.x);
+}
+// multiply by exp(DIR * i * pi/4 * k) for small constant k (used inside radix-8/16)
+template <int DIR, int K8>  // angle = DIR * 2*pi*K8/8
+B2_DEVINL cplx cmul_w8(cplx a) {
+    constexpr double h = 0.70710678118654752440;
+    constexpr int k = ((K8 % 8) + 8) % 8;
+    if (k == 0) return a;
+    if (k == 2) return cmul_i<DIR>(a);
+    if (k == 4) return make_double2(-a.x, -a.y);
+    if (k == 6) return cmul_i<-DIR>(a);
+    // odd k: (c + i s) with |c|=|s|=h
+    const double c = (k == 1 || k == 7) ? h : -h;
+    const double s = (DIR > 0 ? 1.0 : -1.0) * ((k == 1 || k == 3) ? h : -h);
+    return make_double2(a.x * c - a.y * s, a.x * s + a.y * c);
+}
+
+// ---------------------------------------------------------------------------------------
+// butterflies: in-place DFT_R on v[0..R-1], natural order in and out.
+// out[n] = sum_m v[m] * exp(DIR*2*pi*i*m*n/R)
+template <int R, int DIR>
+struct Bfly;
+
+template <int DIR>
+struct Bfly<1, DIR> {
+    static B2_DEVINL void run(cplx*) {}
+};
+
+template <int DIR>
+struct Bfly<2, DIR> {
+    static B2_DEVINL void run(cplx* v) {
+        cplx a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <int DIR>
+struct Bfly<4, DIR> {
+    static B2_DEVINL void run(cplx* v) {
+        cplx t0 = cadd(v[0], v[2]);
+        cplx t1 = csub(v[0], v[2]);
+        cplx t2 = cadd(v[1], v[3]);
+        cplx t3 = cmul_i<DIR>(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2);
+        v[2] = csub(t0, t2);
+        v[1] = cadd(t1, t3);
+        v[3] = csub(t1, t3);
+    }
+};
+
+template <int DIR>
+struct Bfly<8, DIR> {
+    static B2_DEVINL void run(cplx* v) {
+        // decimation in frequency: 8 = 2 x 4
+        cplx u[4], w[4];
+        u[0] = cadd(v[0], v[4]);
+        w[0] = csub(v[0], v[4]);
+        u[1] = cadd(v[1], v[5]);
+        w[1] = cmul_w8<DIR, 1>(csub(v[1], v[5]));
+        u[2] = cadd(v[2], v[6]);
+        w[2] = cmul_w8<DIR, 2>(csub(v[2], v[6]));
+        u[3] = cadd(v[3], v[7]);
+        w[3] = cmul_w8<DIR, 3>(csub(v[3], v[7]));
+        Bfly<4, DIR>::run(u);
+        Bfly<4, DIR>::run(w);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            v[2 * n] = u[n];
+            v[2 * n + 1] = w[n];
+        }
+    }
+};
+
+template <int DIR>
+struct Bfly<16, DIR> {
+    static B2_DEVINL void run(cplx* v) {
+        // 16 = 4 x 4 : columns k (inputs k + 4l), then twiddle W16^(k n), then rows
+        constexpr double c1 = 0.92387953251128675613;  // cos(pi/8)
+        constexpr double s1 = 0.38268343236508977173;  // sin(pi/8)
+        constexpr double sg = DIR > 0 ? 1.0 : -1.0;
+        cplx b[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cplx col[4] = {v[k], v[k + 4], v[k + 8], v[k + 12]};
+            Bfly<4, DIR>::run(col);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) b[k][n] = col[n];
+        }
+        // twiddles W16^(k*n), k,n in 1..3  (k*n in {1,2,3,4,6,9})
+        const cplx w1 = make_double2(c1, sg * s1);
+        const cplx w3 = make_double2(s1, sg * c1);
+        b[1][1] = cmul(b[1][1], w1);
+        b[1][2] = cmul_w8<DIR, 1>(b[1][2]);
+        b[1][3] = cmul(b[1][3], w3);
+        b[2][1] = cmul_w8<DIR, 1>(b[2][1]);
+        b[2][2] = cmul_i<DIR>(b[2][2]);
+        b[2][3] = cmul_w8<DIR, 3>(b[2][3]);
+        b[3][1] = cmul(b[3][1], w3);
+        b[3][2] = cmul_w8<DIR, 3>(b[3][2]);
+        // W16^9 = -W16^1
+        b[3][3] = cmul(b[3][3], make_double2(-c1, -sg * s1));
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            cplx row[4] = {b[0][n], b[1][n], b[2][n], b[3][n]};
+            Bfly<4, DIR>::run(row);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) v[n + 4 * p] = row[p];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// shared-memory exchange plane addressing
+//   logical index w in [0, N) -> padded index w + (w >> 4); TK interleaved columns.
+B2_DEVINL int b2_pad(int w) { return w + (w >> 4); }
+template <int N>
+struct PlaneSize {
+    static constexpr int value = N + (N >> 4) + 1;  // doubles per column per plane
+};
+
+struct SyncBlock {
+    B2_DEVINL void operator()() const { __syncthreads(); }
+};
+struct SyncWarp {
+    B2_DEVINL void operator()() const { __syncwarp(); }
+};
+struct SyncNone {
+    B2_DEVINL void operator()() const {}
+};
+// named barrier over a group of NT threads (NT multiple of 32), id in 1..15
+template <int NT>
+struct SyncNamed {
+    int id;
+    B2_DEVINL void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+};
+
+// Stockham stages.  TWS = stride in the twiddle table (table holds exp(-2 pi i k / (N*TWS))).
+template <int N, int E, int DIR, int TK, int TWS, int Ns, class Sync>
+struct FftStages {
+    static B2_DEVINL void run(cplx (&x)[E], double* __restrict__ sre, double* __restrict__ sim,
+                              int t, int c, const cplx* __restrict__ tw, Sync sync) {
+        constexpr int T = N / E;
+        constexpr int Rem = N / Ns;
+        constexpr int r = Rem >= E ? E : Rem;
+        constexpr int Q = E / r;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            cplx v[r];
+#pragma unroll
+            for (int m = 0; m < r; ++m) v[m] = x[q + m * Q];
+            if (Ns > 1) {
+                const int jm = (t + q * T) & (Ns - 1);
+#pragma unroll
+                for (int m = 1; m < r; ++m) {
+                    cplx w = __ldg(tw + (size_t)(jm * m) * (TWS * (N / (Ns * r))));
+                    if (DIR > 0) w.y = -w.y;
+                    v[m] = cmul(v[m], w);
+                }
+            }
+            Bfly<r, DIR>::run(v);
+#pragma unroll
+            for (int m = 0; m < r; ++m) x[q + m * Q] = v[m];
+        }
+        if constexpr (Ns * r < N) {
+            sync();  // WAR on the planes (previous exchange / previous line)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int j = t + q * T;
+                const int base = (j / Ns) * (Ns * r) + (j & (Ns - 1));
+#pragma unroll
+                for (int m = 0; m < r; ++m) {
+                    const int wp = b2_pad(base + m * Ns) * TK + c;
+                    sre[wp] = x[q + m * Q].x;
+                    sim[wp] = x[q + m * Q].y;
+                }
+            }
+            sync();
+#pragma unroll
+            for (int m = 0; m < E; ++m) {
+                const int pp = b2_pad(t + m * T) * TK + c;
+                x[m] = make_double2(sre[pp], sim[pp]);
+            }
+            FftStages<N, E, DIR, TK, TWS, Ns * r, Sync>::run(x, sre, sim, t, c, tw, sync);
+        }
+    }
+};
+
+// x[m] holds in[t + m*T] on entry and out[t + m*T] on exit (unnormalised).
+template <int N, int E, int DIR, int TK, int TWS, class Sync>
+B2_DEVINL void fft_line(cplx (&x)[E], double* sre, double* sim, int t, int c,
+                        const cplx* __restrict__ tw, Sync sync) {
+    FftStages<N, E, DIR, TK, TWS, 1, Sync>::run(x, sre, sim, t, c, tw, sync);
+}

@@ -1,0 +1,51 @@
+// Internal declarations shared by the translation units of libb200spectral.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200spectral.h"
+#include "fft_core.cuh"
+
+struct b2_plan {
+    int ndim;
+    int n0, n1, n2;  // X shape (2-D plans are stored with n0 == 1)
+    int nk;          // n2/2 + 1
+    double L0, L1, L2;
+    bool fast0, fast1, fast2;  // register-FFT path available along that axis
+    cplx *tw0, *tw1, *tw2;     // exp(-2 pi i k / n) tables (device)
+    double *k0, *k1, *kx;      // dimensional wavenumbers along K axes 0, 1, 2 (device)
+    // physics (b2_set_physics)
+    int solver;
+    double nu2, nu4, nu8, num4, f, N, beta;
+    int has_f;
+    const uint8_t* mask;
+    // caller-owned buffers (b2_set_buffers)
+    cplx *acc, *stage, *work;
+    long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
+    long long xsize() const { return (long long)n0 * n1 * n2; }
+};
+
+int b2i_set_error(const char* fmt, ...);
+int b2i_check_launch(const char* what);
+void b2i_count_launch();
+
+#define B2_LAUNCH_CHECK(what)                     \
+    do {                                          \
+        b2i_count_launch();                       \
+        int _e = b2i_check_launch(what);          \
+        if (_e) return _e;                        \
+    } while (0)
+
+// --- strided passes (strided.cu).  axis: 0 (z, skipped when n0 == 1) or 1 (y).  dir: -1 fwd, +1 inv.
+int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx* const* out, int nf,
+                      double scale, cudaStream_t s);
+// first inverse pass of a stage with the k-space prologue fused on load:
+//   ns3d / strat : in = nvar stage-input fields; out = W[0..2] = v, W[3..5] = curl v (+f), W[6] = b
+//   ns2d         : in = rot; out = W[0]=ux, W[1]=uy, W[2]=d_x rot, W[3]=d_y rot
+int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, cudaStream_t s);
+
+// --- x passes (xpass.cu)
+int b2i_xpass_c2r(b2_plan* p, const cplx* K, double* X, cudaStream_t s);
+int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream_t s);
+// fused c2r -> product -> r2c for p->solver; W fields as produced by b2i_first_inverse_pass
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, double scale, cudaStream_t s);

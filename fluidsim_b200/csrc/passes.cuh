@@ -1,0 +1,293 @@
+// FFT pass kernels (float64 / complex128) built on fft_core.cuh.
+//
+//  * fft_strided_kernel   batched complex FFT along a strided axis (y or z pass).  A CTA owns a
+//                         tile of TK adjacent columns (contiguous in memory -> every global access
+//                         is a TK*16-byte segment) and the whole line along the FFT axis.
+//                         LoadOp / StoreOp functors fuse k-space prologues / epilogues.
+//  * xpass_*_kernel       contiguous-axis pass: c2r, r2c and the fused
+//                         c2r x NI -> pointwise product -> r2c x NO kernel.
+//  * fft_generic_kernel   any line length (mixed radix, O(N * sum(prime factors)) in shared
+//                         memory) -- the non power-of-two path used by the operator-level API.
+//
+// Replaces fluidfft's fft_as_arg / ifft_as_arg / vector_product call chain
+// (/root/reference/fluidsim/solvers/ns3d/solver.py:199-241).
+#pragma once
+#include "fft_core.cuh"
+
+struct Geom {
+    int ncols;      // number of columns (contiguous index)
+    int nouter;     // number of outer batches
+    long long es;   // stride (elements) between successive points of a line
+    long long os;   // stride (elements) between outer batches
+    long long cs;   // stride between columns (1 for the fast path)
+};
+
+#define B2_MAXF 8
+
+// ------------------------------------------------------------------------------- load/store ops
+struct PlainLoad {
+    const cplx* in[B2_MAXF];
+    B2_DEVINL cplx operator()(int f, long long off, int i, int col, int outer) const {
+        return in[f][off];
+    }
+};
+struct PlainStore {
+    cplx* out[B2_MAXF];
+    B2_DEVINL void operator()(int f, long long off, int i, int col, int outer, cplx v) const {
+        out[f][off] = v;
+    }
+};
+struct ScaleStore {
+    cplx* out[B2_MAXF];
+    double scale;
+    B2_DEVINL void operator()(int f, long long off, int i, int col, int outer, cplx v) const {
+        out[f][off] = cscale(v, scale);
+    }
+};
+
+// ------------------------------------------------------------------------------- strided pass
+template <int N, int E, int TK, int DIR, class LoadOp, class StoreOp>
+__global__ void __launch_bounds__(TK*(N / E))
+    fft_strided_kernel(Geom g, LoadOp ld, StoreOp st, const cplx* __restrict__ tw) {
+    extern __shared__ double b2_smem[];
+    constexpr int T = N / E;
+    constexpr int PS = PlaneSize<N>::value * TK;
+    double* sre = b2_smem;
+    double* sim = b2_smem + PS;
+    const int c = threadIdx.x % TK;
+    const int t = threadIdx.x / TK;
+    const int col = blockIdx.x * TK + c;
+    const int outer = blockIdx.y;
+    const int field = blockIdx.z;
+    const bool active = col < g.ncols;
+    const long long base = (long long)outer * g.os + col;
+    cplx x[E];
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int i = t + m * T;
+        x[m] = active ? ld(field, base + (long long)i * g.es, i, col, outer) : make_double2(0.0, 0.0);
+    }
+    fft_line<N, E, DIR, TK, 1>(x, sre, sim, t, c, tw, SyncBlock());
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int i = t + m * T;
+            st(field, base + (long long)i * g.es, i, col, outer, x[m]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------- x pass pieces
+// c2r along a contiguous line of N reals (M = N/2 complex FFT).  On exit x[m] = (u[2n], u[2n+1]),
+// n = t + m*T.  Unnormalised (FFTW c2r convention).  Imaginary parts of k=0 and k=N/2 are ignored.
+template <int N, int E, class Sync>
+B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, double* sre, double* sim, int t,
+                        const cplx* __restrict__ twN, Sync sync) {
+    constexpr int M = N / 2, T = M / E;
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int k = t + m * T;
+        const cplx a = K[k];
+        const cplx b = K[M - k];
+        if (k == 0) {
+            x[m] = make_double2(a.x + b.x, a.x - b.x);
+        } else {
+            const cplx s = make_double2(a.x + b.x, a.y - b.y);  // a + conj(b)
+            const cplx d = make_double2(a.x - b.x, a.y + b.y);  // a - conj(b)
+            cplx w = __ldg(twN + k);
+            w.y = -w.y;  // exp(+2 pi i k / N)
+            const cplx e = cmul(d, w);
+            x[m] = make_double2(s.x - e.y, s.y + e.x);  // s + i e
+        }
+    }
+    fft_line<M, E, +1, 1, 2>(x, sre, sim, t, 0, twN, sync);
+}
+
+// r2c: x[m] = (u[2n], u[2n+1]) on entry; writes K[0..M] scaled by `scale`.
+template <int N, int E, class Sync>
+B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, double* sre, double* sim, int t,
+                        const cplx* __restrict__ twN, Sync sync, double scale, bool do_store) {
+    constexpr int M = N / 2, T = M / E;
+    fft_line<M, E, -1, 1, 2>(x, sre, sim, t, 0, twN, sync);
+    sync();
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int p = b2_pad(t + m * T);
+        sre[p] = x[m].x;
+        sim[p] = x[m].y;
+    }
+    sync();
+    const double hs = 0.5 * scale;
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int k = t + m * T;
+        if (k == 0) {
+            if (do_store) {
+                K[0] = make_double2((x[m].x + x[m].y) * scale, 0.0);
+                K[M] = make_double2((x[m].x - x[m].y) * scale, 0.0);
+            }
+        } else {
+            const int p = b2_pad(M - k);
+            const cplx zc = make_double2(sre[p], -sim[p]);  // conj(Z[M-k])
+            const cplx s = cadd(x[m], zc);
+            const cplx d = csub(x[m], zc);
+            const cplx w = __ldg(twN + k);
+            const cplx e = cmul(d, w);
+            if (do_store) K[k] = make_double2((s.x + e.y) * hs, (s.y - e.x) * hs);
+        }
+    }
+}
+
+template <int N, int E>
+struct XSync {
+    static constexpr int T = (N / 2) / E;
+};
+
+// plain c2r : K (nlines, M+1) -> X (nlines, N)
+template <int N, int E, int LPB>
+__global__ void __launch_bounds__(LPB*((N / 2) / E))
+    xpass_c2r_kernel(const cplx* __restrict__ K, double* __restrict__ X, long long nlines,
+                     const cplx* __restrict__ twN) {
+    extern __shared__ double b2_smem[];
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    const int ls = threadIdx.x / T, t = threadIdx.x % T;
+    long long line = (long long)blockIdx.x * LPB + ls;
+    const bool active = line < nlines;
+    if (!active) line = nlines - 1;
+    double* sre = b2_smem + (size_t)ls * 2 * PS;
+    double* sim = sre + PS;
+    cplx x[E];
+    c2r_line<N, E>(x, K + line * (M + 1), sre, sim, t, twN, SyncBlock());
+    if (active) {
+        double2* out = reinterpret_cast<double2*>(X + line * N);
+#pragma unroll
+        for (int m = 0; m < E; ++m) out[t + m * T] = x[m];
+    }
+}
+
+// plain r2c : X (nlines, N) -> K (nlines, M+1), scaled
+template <int N, int E, int LPB>
+__global__ void __launch_bounds__(LPB*((N / 2) / E))
+    xpass_r2c_kernel(const double* __restrict__ X, cplx* __restrict__ K, long long nlines,
+                     const cplx* __restrict__ twN, double scale) {
+    extern __shared__ double b2_smem[];
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    const int ls = threadIdx.x / T, t = threadIdx.x % T;
+    long long line = (long long)blockIdx.x * LPB + ls;
+    const bool active = line < nlines;
+    if (!active) line = nlines - 1;
+    double* sre = b2_smem + (size_t)ls * 2 * PS;
+    double* sim = sre + PS;
+    cplx x[E];
+    const double2* in = reinterpret_cast<const double2*>(X + line * N);
+#pragma unroll
+    for (int m = 0; m < E; ++m) x[m] = in[t + m * T];
+    r2c_line<N, E>(x, K + line * (M + 1), sre, sim, t, twN, SyncBlock(), scale, active);
+}
+
+// fused: NI spectral lines -> c2r -> pointwise Op -> r2c -> NO spectral lines.
+// Op: struct with static NI, NO; in[NI], out[NO] pointers (field bases);
+//     __device__ void point(const double* u /*NI*/, double* r /*NO*/) const.
+// Physical values are parked in thread-private shared-memory slots between transforms.
+template <int N, int E, int LPB, class Op>
+__global__ void __launch_bounds__(LPB*((N / 2) / E))
+    xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
+    extern __shared__ double b2_smem[];
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int NI = Op::NI, NO = Op::NO;
+    constexpr int PER_LS = 2 * PS + 2 * NI * M;  // doubles per line-set
+    const int ls = threadIdx.x / T, t = threadIdx.x % T;
+    long long line = (long long)blockIdx.x * LPB + ls;
+    const bool active = line < nlines;
+    if (!active) line = nlines - 1;
+    double* sre = b2_smem + (size_t)ls * PER_LS;
+    double* sim = sre + PS;
+    cplx* park = reinterpret_cast<cplx*>(sre + 2 * PS);
+    const long long loff = line * (M + 1);
+    cplx x[E];
+#pragma unroll 1
+    for (int f = 0; f < NI; ++f) {
+        c2r_line<N, E>(x, op.in[f] + loff, sre, sim, t, twN, SyncBlock());
+#pragma unroll
+        for (int m = 0; m < E; ++m) park[(f * E + m) * T + t] = x[m];
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        double ue[NI], uo[NI], re[NO], ro[NO];
+#pragma unroll
+        for (int f = 0; f < NI; ++f) {
+            const cplx v = park[(f * E + m) * T + t];
+            ue[f] = v.x;
+            uo[f] = v.y;
+        }
+        op.point(ue, re);
+        op.point(uo, ro);
+#pragma unroll
+        for (int o = 0; o < NO; ++o) park[(o * E + m) * T + t] = make_double2(re[o], ro[o]);
+    }
+#pragma unroll 1
+    for (int o = 0; o < NO; ++o) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) x[m] = park[(o * E + m) * T + t];
+        r2c_line<N, E>(x, op.out[o] + loff, sre, sim, t, twN, SyncBlock(), scale, active);
+    }
+}
+
+// ------------------------------------------------------------------------------- generic length
+struct GenericFactors {
+    int nfac;
+    int fac[24];
+};
+
+// dynamic smem: 2 * N * TK complex
+template <int DIR, class LoadOp, class StoreOp>
+__global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
+                                   const cplx* __restrict__ tw, GenericFactors gf) {
+    extern __shared__ double b2_smem[];
+    cplx* a = reinterpret_cast<cplx*>(b2_smem);
+    cplx* b = a + (size_t)N * TK;
+    const int outer = blockIdx.y, field = blockIdx.z;
+    const int col0 = blockIdx.x * TK;
+    for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
+        const int i = idx / TK, c = idx % TK, col = col0 + c;
+        cplx v = make_double2(0.0, 0.0);
+        if (col < g.ncols)
+            v = ld(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer);
+        a[idx] = v;
+    }
+    __syncthreads();
+    int Ns = 1;
+    for (int s = 0; s < gf.nfac; ++s) {
+        const int r = gf.fac[s];
+        const int nb = N / r;
+        const int tws = N / (Ns * r);
+        for (int idx = threadIdx.x; idx < nb * TK; idx += blockDim.x) {
+            const int j = idx / TK, c = idx % TK;
+            const int jm = j % Ns;
+            const int base_out = (j / Ns) * Ns * r + jm;
+            for (int n = 0; n < r; ++n) {
+                cplx acc = make_double2(0.0, 0.0);
+                for (int m = 0; m < r; ++m) {
+                    const long long ph = ((long long)jm * m * tws + (long long)m * n * nb) % N;
+                    cplx w = tw[ph];
+                    if (DIR > 0) w.y = -w.y;
+                    const cplx v = a[(size_t)(j + m * nb) * TK + c];
+                    acc.x += v.x * w.x - v.y * w.y;
+                    acc.y += v.x * w.y + v.y * w.x;
+                }
+                b[(size_t)(base_out + n * Ns) * TK + c] = acc;
+            }
+        }
+        __syncthreads();
+        cplx* tmp = a;
+        a = b;
+        b = tmp;
+        Ns *= r;
+    }
+    for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
+        const int i = idx / TK, c = idx % TK, col = col0 + c;
+        if (col < g.ncols)
+            st(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer,
+               a[idx]);
+    }
+}

@@ -1,0 +1,140 @@
+/* b200spectral.h -- C ABI of libb200spectral.so (B200 / sm_100a pseudo-spectral hot path).
+ *
+ * Drop-in boundary for fluidsim's pseudo-spectral time step.  Every entry point takes raw DEVICE
+ * pointers (float64 / complex128 = double[2], C-contiguous, the reference's array shapes) plus a
+ * cudaStream_t passed as void*; returns 0 on success, <0 on error (message: b2_last_error()).
+ * Nothing here allocates field-sized memory: state, accumulators and work buffers are caller-owned
+ * (PyTorch tensors on the Python side).  No torch types cross this boundary.
+ *
+ * Array conventions (sequential layout, the one fluidfft's `fft3d.with_pyfftw` exposes,
+ * /root/reference/fluidsim/operators/operators3d.py:120-133):
+ *   3-D:  X (n0=nz, n1=ny, n2=nx) float64      K (n0, n1, n2/2+1) complex128, dimX_K = (0,1,2)
+ *   2-D:  X (n0=ny, n1=nx)         float64      K (n0, n1/2+1)     complex128, not transposed
+ * Forward transform is scaled by 1/(n0*n1*n2); inverse is unscaled (fluidfft convention,
+ * /root/reference/fluidsim/base/state.py:385-392 relies on it).
+ *
+ * Each function names the reference interface it replaces (paths relative to
+ * /root/reference/fluidsim/).
+ */
+#ifndef B200SPECTRAL_H
+#define B200SPECTRAL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_plan b2_plan;
+
+/* solver ids for b2_set_physics */
+#define B2_SOLVER_NS3D 0       /* solvers/ns3d/solver.py:180-253        */
+#define B2_SOLVER_NS3D_STRAT 1 /* solvers/ns3d/strat/solver.py:138-216  */
+#define B2_SOLVER_NS2D 2       /* solvers/ns2d/solver.py:111-194        */
+
+/* time schemes for b2_time_step */
+#define B2_SCHEME_RK2 2 /* base/time_stepping/pseudo_spect.py:469-517 */
+#define B2_SCHEME_RK4 4 /* base/time_stepping/pseudo_spect.py:798-984 */
+
+const char* b2_last_error(void);
+int b2_version(void);
+
+/* ---- plan: replaces fluidfft.create_fft_object(type_fft, n0, n1, n2) + the K-grid part of
+ * OperatorsPseudoSpectral3D.__init__ (operators/operators3d.py:207-231).  ndim = 2 or 3; for
+ * ndim == 2 pass n2 = 0 and L2 = 0 (n0 = ny, n1 = nx).  L0, L1, L2 are the box lengths along the
+ * X axes (Lz, Ly, Lx) resp. (Ly, Lx). */
+int b2_plan_create(b2_plan** out, int ndim, int n0, int n1, int n2, double L0, double L1, double L2);
+int b2_plan_destroy(b2_plan* p);
+/* shapeX[3], shapeK[3] (2-D: leading entry is 1): get_shapeX_seq / get_shapeK_seq */
+int b2_plan_shapes(const b2_plan* p, int* shapeX, int* shapeK);
+/* 1 if the fused register-FFT path handles these sizes (all axes powers of two >= 8) */
+int b2_plan_is_fast(const b2_plan* p);
+
+/* ---- transforms: replace fft_as_arg / ifft_as_arg / ifft_as_arg_destroy
+ * (solvers/ns3d/solver.py:210-241, base/state.py:318-332).
+ * b2_ifft_c2r: `work` is a K-sized complex scratch; pass NULL to transform in place in K
+ * (ifft_as_arg_destroy semantics: K is clobbered). */
+int b2_fft_r2c(b2_plan* p, const double* X, double* K, void* stream);
+int b2_ifft_c2r(b2_plan* p, const double* K, double* X, double* work, void* stream);
+
+/* ---- k-space / x-space operator kernels (fluidfft operator methods) */
+/* rotfft_from_vecfft_outin: solvers/ns3d/solver.py:199 */
+int b2_rotfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const double* vz,
+                          double* rx, double* ry, double* rz, void* stream);
+/* divfft_from_vecfft: used by div_vb_fft_from_vb, solvers/ns3d/strat/solver.py:206 */
+int b2_divfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const double* vz,
+                          double* div, void* stream);
+/* project_perpk3d: solvers/ns3d/solver.py:255-259 (in place) */
+int b2_project_perpk3d(b2_plan* p, double* vx, double* vy, double* vz, void* stream);
+/* vector_product(a, b) -> written into b: solvers/ns3d/solver.py:226 */
+int b2_vector_product(const double* ax, const double* ay, const double* az, double* bx, double* by,
+                      double* bz, long long n, void* stream);
+/* out = a * b (real fields): v_i * b products of div_vb_fft_from_vb */
+int b2_mul_real(const double* a, const double* b, double* out, long long n, void* stream);
+/* dealiasing_setofvar / dealiasing_variable: operators/operators3d.py:38-71, 336-342.
+ * fields = nvar contiguous K arrays; mask = uint8 K-shaped (where_dealiased). */
+int b2_dealias(b2_plan* p, double* fields, int nvar, const uint8_t* mask, void* stream);
+/* 2-D: vecfft_from_rotfft, gradfft_from_fft (solvers/ns2d/solver.py:158,165), compute_Frot (:34-38) */
+int b2_vecfft_from_rotfft2d(b2_plan* p, const double* rot, double* ux, double* uy, void* stream);
+int b2_gradfft_from_fft2d(b2_plan* p, const double* f, double* px, double* py, void* stream);
+int b2_rotfft_from_vecfft2d(b2_plan* p, const double* ux, const double* uy, double* rot, void* stream);
+int b2_compute_frot(const double* ux, const double* uy, const double* px, const double* py, double beta,
+                    double* out, long long n, void* stream);
+/* compute_fb_fft: solvers/ns3d/strat/solver.py:29-33 : fb = -div_vb - N^2 vz (in place in div_vb) */
+int b2_compute_fb_fft(double* div_vb, double N, const double* vz, long long nk, void* stream);
+/* a += b (complex arrays of nk elements): `fz_fft += b_fft`, strat/solver.py:198 */
+int b2_add_inplace(double* a, const double* b, long long nk, void* stream);
+
+/* ---- linear term + elementwise RK kernels (base/time_stepping/pseudo_spect.py) */
+/* compute_freq_diss (base/solvers/pseudo_spect.py:134-191) + ExactLinearCoefs.compute (:122-141):
+ * exact = exp(-dt*sigma), exact2 = exp(-dt/2*sigma), real K-shaped */
+int b2_exact_coefs(b2_plan* p, double nu2, double nu4, double nu8, double num4, double dt, double* exact,
+                   double* exact2, void* stream);
+/* step_Euler :51-56   out = (S + dt*T) * diss   (nvar fields, diss broadcast over nvar) */
+int b2_step_euler(b2_plan* p, const double* S, double dt, const double* T, const double* diss,
+                  double* out, int nvar, void* stream);
+/* step_like_RK2 :64-68   S = S*diss + dt*diss2*T */
+int b2_step_like_rk2(b2_plan* p, double* S, double dt, const double* T, const double* diss,
+                     const double* diss2, int nvar, void* stream);
+/* rk4_step1 :938-941   acc += dt/3*diss2*T ; S12 = S*diss2 + dt/2*T */
+int b2_rk4_step1(b2_plan* p, const double* S, double* acc, double* S12, const double* T,
+                 const double* diss2, double dt, int nvar, void* stream);
+/* rk4_step2 :968-971   acc += dt/3*diss2*T ; S1 = S*diss + dt*diss2*T */
+int b2_rk4_step2(b2_plan* p, const double* S, double* acc, double* S1, const double* T,
+                 const double* diss, const double* diss2, double dt, int nvar, void* stream);
+/* rk4_step3 :984   S = acc + dt/6*T */
+int b2_rk4_step3(b2_plan* p, double* S, const double* acc, const double* T, double dt, int nvar,
+                 void* stream);
+
+/* ---- reductions */
+/* sum_wavenumbers(|f|^2) over nvar fields (r2c-aware weights), result written to *out_dev (device
+ * double).  compute_energy_from_K = 0.5 * this. */
+int b2_sum_wavenumbers_abs2(b2_plan* p, const double* fields, int nvar, double* out_dev, void* stream);
+/* max |x| over n doubles -> *out_dev : _compute_time_increment_CLF_uxuyuz, base/time_stepping/base.py:320-339 */
+int b2_max_abs(const double* x, long long n, double* out_dev, void* stream);
+/* sum of all doubles (NaN check `np.isnan(np.sum(state_spect[0]))`, solvers/ns3d/time_stepping.py:19) */
+int b2_sum(const double* x, long long n, double* out_dev, void* stream);
+
+/* ---- fused path: replaces Simul.tendencies_nonlin + TimeSteppingPseudoSpectral._time_step_RK2/4 +
+ * one_time_step_computation's project/dealias (solvers/ns3d/time_stepping.py:8-20). */
+/* physics parameters: params.nu_2/4/8/m4, params.f (has_f=0 -> None), params.N, params.beta;
+ * mask = where_dealiased (uint8, K-shaped, device; may be NULL = no dealiasing) */
+int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4, int has_f,
+                   double f, double N, double beta, const uint8_t* mask);
+/* number of K-sized complex work fields the fused path needs for this solver (W), nvar of state */
+int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar);
+/* caller-owned buffers: acc, stage (each nvar K-fields), work (nwork K-fields) */
+int b2_set_buffers(b2_plan* p, double* acc, double* stage, double* work);
+/* T_out = N(S_in)  (projected + dealiased).  S_in is preserved; T_out may not alias S_in. */
+int b2_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream);
+/* one full step of `scheme` with time increment dt, in place on S, including the final
+ * project_state_spect + dealiasing of one_time_step_computation. */
+int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
+/* kernels launched by this library since load (for bench.py's gpu_launches) */
+long long b2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
