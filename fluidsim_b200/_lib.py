@@ -65,6 +65,9 @@ SIGNATURES = {
     "b2_set_buffers": [_p, _p, _p, _p],
     "b2_tendencies": [_p, _p, _p, _p],
     "b2_time_step": [_p, _i, _d, _p, _p],
+    "b2_profile_enable": [_i],
+    "b2_profile_reset": [],
+    "b2_profile_get": [C.POINTER(_d), C.POINTER(_ll), _i],
 }
 _RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": _ll}
 

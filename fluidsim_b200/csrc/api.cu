@@ -591,6 +591,71 @@ extern "C" int b2_sum(const double* x, long long n, double* out_dev, void* strea
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------- profiling hooks
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
+// leg).  Disabled by default: zero overhead unless b2_profile_enable(1) was called.
+enum { PC_FIRST_INV = 0, PC_Y_INV, PC_X_FUSED, PC_Y_FWD, PC_Z_FWD, PC_RK, PC_COUNT };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[PC_COUNT];
+static long long g_prof_n[PC_COUNT];
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    bool on;
+    ProfRec r;
+    cudaStream_t s;
+    ProfScope(int cat, cudaStream_t s_) : on(g_prof_on), s(s_) {
+        if (!on) return;
+        r.cat = cat;
+        r.a = prof_event();
+        r.b = prof_event();
+        cudaEventRecord(r.a, s);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(r.b, s);
+        g_prof_recs.push_back(r);
+    }
+};
+extern "C" int b2_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+extern "C" int b2_profile_reset(void) {
+    for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+    for (int i = 0; i < PC_COUNT; ++i) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+    return 0;
+}
+// synchronises the device, folds pending records; ms[cat], count[cat] for cat < ncat
+extern "C" int b2_profile_get(double* ms, long long* count, int ncat) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& r : g_prof_recs) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        g_prof_ms[r.cat] += t;
+        g_prof_n[r.cat] += 1;
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof_recs.clear();
+    for (int i = 0; i < ncat && i < PC_COUNT; ++i) { ms[i] = g_prof_ms[i]; count[i] = g_prof_n[i]; }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------- fused path
 extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4,
                               int has_f, double f, double N, double beta, const uint8_t* mask) {
@@ -743,6 +808,7 @@ static int launch_rk_stage_s(int mode, const RKArgs& a, unsigned grid, cudaStrea
 }
 
 static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s) {
+    ProfScope ps(PC_RK, s);
     const unsigned grid = nrows(p);
     switch (p->solver) {
         case B2_SOLVER_NS3D: return launch_rk_stage_s<B2_SOLVER_NS3D>(mode, a, grid, s);
@@ -765,12 +831,26 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, cudaStream_t s) {
     const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
     const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
     int e;
-    if ((e = b2i_first_inverse_pass(p, in, W, s))) return e;
-    if (p->n0 > 1)
+    {
+        ProfScope ps(PC_FIRST_INV, s);
+        if ((e = b2i_first_inverse_pass(p, in, W, s))) return e;
+    }
+    if (p->n0 > 1) {
+        ProfScope ps(PC_Y_INV, s);
         if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s))) return e;
-    if ((e = b2i_xpass_fused(p, W, scale, s))) return e;
-    if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s))) return e;
-    if ((e = b2i_strided_plain(p, 0, -1, Wc, W, nout, 1.0, s))) return e;
+    }
+    {
+        ProfScope ps(PC_X_FUSED, s);
+        if ((e = b2i_xpass_fused(p, W, scale, s))) return e;
+    }
+    {
+        ProfScope ps(PC_Y_FWD, s);
+        if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s))) return e;
+    }
+    if (p->n0 > 1) {
+        ProfScope ps(PC_Z_FWD, s);
+        if ((e = b2i_strided_plain(p, 0, -1, Wc, W, nout, 1.0, s))) return e;
+    }
     return 0;
 }
 

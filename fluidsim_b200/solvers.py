@@ -1,0 +1,276 @@
+"""GPU ``Simul`` classes for ns3d, ns3d.strat and ns2d.
+
+Host-side mirror of ``/root/reference/fluidsim/solvers/ns3d/solver.py:57-263``,
+``solvers/ns3d/strat/solver.py:57-216`` and ``solvers/ns2d/solver.py:73-194`` reduced to the hot
+path: construction order Operators -> State -> TimeStepping (``base/solvers/base.py:117-223``),
+``tendencies_nonlin(state_spect=None, old=None)``, ``project_state_spect``,
+``compute_freq_diss``.  Same names, same argument meaning, same exceptions; arrays are CUDA
+tensors and all arithmetic is done by libb200spectral kernels.
+"""
+
+import numpy as np
+import torch
+
+from ._lib import SOLVER_IDS, call, lib, ptr, stream_ptr
+from .operators import OperatorsPseudoSpectral2D, OperatorsPseudoSpectral3D, vector_product
+from .params import create_default_params
+from .setofvariables import SetOfVariables
+from .state import StateNS2D, StateNS3D, StateNS3DStrat
+from .time_stepping import TimeSteppingPseudoSpectralB200
+
+
+class SimulBasePseudoSpectralB200:
+    short_name = None
+    ndim = 3
+    Operators = OperatorsPseudoSpectral3D
+    State = StateNS3D
+    TimeStepping = TimeSteppingPseudoSpectralB200
+
+    @classmethod
+    def create_default_params(cls):
+        return create_default_params(cls.short_name)
+
+    def __init__(self, params, fused=None):
+        self.params = params
+        self.is_forcing_enabled = bool(getattr(params.forcing, "enable", False))
+        if self.is_forcing_enabled:
+            raise NotImplementedError("forcing is outside the GPU hot path (SURVEY.md section 8 f-2)")
+        self.oper = self.Operators(params)
+        self.state = self.State(self)
+        self._init_projection()
+        self._fused_buffers = None
+        self._fused_mask = None
+        self.time_stepping = self.TimeStepping(self, fused=fused)
+
+    def _init_projection(self):
+        pass
+
+    # ---- fused path plumbing -------------------------------------------------------------------------
+    def _physics_args(self):
+        p = self.params
+        f = getattr(p, "f", None)
+        return (
+            float(p.nu_2), float(p.nu_4), float(p.nu_8), float(p.nu_m4),
+            0 if f is None else 1, 0.0 if f is None else float(f),
+            float(getattr(p, "N", 0.0)), float(getattr(p, "beta", 0.0)),
+        )
+
+    def _mask_for_fused(self):
+        oper = self.oper
+        if self.ndim == 2 and not oper._has_to_dealiase:
+            return None
+        return oper.where_dealiased
+
+    def _ensure_fused_buffers(self):
+        """Allocate acc / stage / work buffers (caller-owned by the C ABI) and push the physics."""
+        mask = self._mask_for_fused()
+        if self._fused_buffers is not None and self._fused_mask is mask:
+            return
+        oper = self.oper
+        h = oper.plan.handle
+        import ctypes as C
+
+        nwork, nvar = C.c_int(), C.c_int()
+        call("b2_work_fields", h, SOLVER_IDS[self.short_name], C.byref(nwork), C.byref(nvar))
+        if self._fused_buffers is None:
+            mk = lambda n: torch.empty((n,) + tuple(oper.shapeK_loc), dtype=torch.complex128, device=oper.device)
+            self._fused_buffers = (mk(nvar.value), mk(nvar.value), mk(nwork.value))
+        acc, stage, work = self._fused_buffers
+        self._fused_mask = mask
+        call("b2_set_physics", h, SOLVER_IDS[self.short_name], *self._physics_args(), ptr(mask))
+        call("b2_set_buffers", h, ptr(acc), ptr(stage), ptr(work))
+
+    def tendencies_nonlin_fused(self, state_spect=None, old=None):
+        """N(state_spect) through the fused kernels (C ABI ``b2_tendencies``)."""
+        self._ensure_fused_buffers()
+        src = self.state.state_spect if state_spect is None else state_spect
+        tendencies_fft = SetOfVariables(like=self.state.state_spect, info="tendencies_nonlin") if old is None else old
+        call("b2_tendencies", self.oper.plan.handle, ptr(src.tensor), ptr(tendencies_fft.tensor), stream_ptr())
+        return tendencies_fft
+
+    # ---- linear term (base/solvers/pseudo_spect.py:134-191) -----------------------------------------
+    def compute_freq_diss(self):
+        p = self.params
+        oper = self.oper
+        K2 = oper.K2
+        f_d = p.nu_2 * K2 if p.nu_2 > 0 else torch.zeros_like(K2)
+        if p.nu_4 > 0.0:
+            f_d = f_d + p.nu_4 * K2**2
+        if p.nu_8 > 0.0:
+            f_d = f_d + p.nu_8 * K2**4
+        if p.nu_m4 != 0.0:
+            f_d_hypo = p.nu_m4 / oper.K2_not0**2
+            if self.ndim == 2:
+                f_d_hypo[0, 0] = f_d_hypo[0, 1]
+            else:
+                f_d_hypo[0, 0, 0] = f_d_hypo[0, 0, 1]
+        else:
+            f_d_hypo = 0.0
+        return f_d, f_d_hypo
+
+
+class SimulNS3D(SimulBasePseudoSpectralB200):
+    """solvers/ns3d/solver.py:57-263."""
+
+    short_name = "ns3d"
+
+    def __init__(self, params, fused=None):
+        super().__init__(params, fused=fused)
+        oper = self.oper
+        # solvers/ns3d/state.py:46-52 (allocated lazily: only the unfused path needs them)
+        self._fields_tmp = None
+        self._fields_spect_tmp = None
+
+    def _init_projection(self):
+        """solver.py:147-174: only the default projection is on the GPU path."""
+        if getattr(self.params, "no_vz_kz0", False):
+            raise NotImplementedError("no_vz_kz0 is not implemented on the GPU path")
+        projection = getattr(self.params, "projection", None)
+        if projection is None:
+            self._projector = self.oper.project_perpk3d
+        elif projection in ("toroidal", "vortical", "poloidal"):
+            raise NotImplementedError(f"projection = {projection!r} is not implemented on the GPU path")
+        else:
+            raise ValueError(f"No known projection for params.projection = {projection}")
+
+    @property
+    def fields_tmp(self):
+        if self._fields_tmp is None:
+            self._fields_tmp = tuple(self.oper.create_arrayX() for _ in range(6))
+        return self._fields_tmp
+
+    @property
+    def fields_spect_tmp(self):
+        if self._fields_spect_tmp is None:
+            self._fields_spect_tmp = tuple(self.oper.create_arrayK() for _ in range(3))
+        return self._fields_spect_tmp
+
+    def _modif_omegafft_with_f(self, omegax_fft, omegay_fft, omegaz_fft):
+        omegaz_fft[0, 0, 0] += self.params.f
+
+    def tendencies_nonlin(self, state_spect=None, old=None):
+        """solver.py:180-253, executed with operator-level kernels (any grid size)."""
+        oper = self.oper
+        ifft_as_arg = oper.ifft_as_arg
+        ifft_as_arg_destroy = oper.ifft_as_arg_destroy
+        fft_as_arg = oper.fft_as_arg
+        spect_get_var = (self.state.state_spect if state_spect is None else state_spect).get_var
+        vx_fft = spect_get_var("vx_fft")
+        vy_fft = spect_get_var("vy_fft")
+        vz_fft = spect_get_var("vz_fft")
+        omegax_fft, omegay_fft, omegaz_fft = self.fields_spect_tmp
+        oper.rotfft_from_vecfft_outin(vx_fft, vy_fft, vz_fft, omegax_fft, omegay_fft, omegaz_fft)
+        if self.params.f is not None:
+            self._modif_omegafft_with_f(omegax_fft, omegay_fft, omegaz_fft)
+        omegax, omegay, omegaz = self.fields_tmp[3:6]
+        ifft_as_arg_destroy(omegax_fft, omegax)
+        ifft_as_arg_destroy(omegay_fft, omegay)
+        ifft_as_arg_destroy(omegaz_fft, omegaz)
+        if state_spect is None:
+            vx = self.state.state_phys.get_var("vx")
+            vy = self.state.state_phys.get_var("vy")
+            vz = self.state.state_phys.get_var("vz")
+        else:
+            vx, vy, vz = self.fields_tmp[0:3]
+            ifft_as_arg(vx_fft, vx)
+            ifft_as_arg(vy_fft, vy)
+            ifft_as_arg(vz_fft, vz)
+        fx, fy, fz = vector_product(vx, vy, vz, omegax, omegay, omegaz)
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state.state_spect, info="tendencies_nonlin")
+        else:
+            tendencies_fft = old
+        fft_as_arg(fx, tendencies_fft.get_var("vx_fft"))
+        fft_as_arg(fy, tendencies_fft.get_var("vy_fft"))
+        fft_as_arg(fz, tendencies_fft.get_var("vz_fft"))
+        self._extra_tendencies(tendencies_fft, spect_get_var, state_spect, vx, vy, vz)
+        self.project_state_spect(tendencies_fft)
+        self.oper.dealiasing(tendencies_fft)
+        return tendencies_fft
+
+    def _extra_tendencies(self, tendencies_fft, spect_get_var, state_spect, vx, vy, vz):
+        pass
+
+    def project_state_spect(self, state_spect):
+        """solver.py:255-263."""
+        self._projector(
+            state_spect.get_var("vx_fft"), state_spect.get_var("vy_fft"), state_spect.get_var("vz_fft")
+        )
+
+
+class SimulNS3DStrat(SimulNS3D):
+    """solvers/ns3d/strat/solver.py:57-216."""
+
+    short_name = "ns3d.strat"
+    State = StateNS3DStrat
+
+    def _extra_tendencies(self, tendencies_fft, spect_get_var, state_spect, vx, vy, vz):
+        """strat/solver.py:198-211: fz += b ; fb = -div(v b) - N^2 vz."""
+        oper = self.oper
+        b_fft = spect_get_var("b_fft")
+        vz_fft = spect_get_var("vz_fft")
+        fz_fft = tendencies_fft.get_var("vz_fft")
+        call("b2_add_inplace", ptr(fz_fft), ptr(b_fft), fz_fft.numel(), stream_ptr())
+        if state_spect is None:
+            b = self.state.state_phys.get_var("b")
+        else:
+            b = self.fields_tmp[3]
+            oper.ifft_as_arg(b_fft, b)
+        div_vb_fft = oper.div_vb_fft_from_vb(vx, vy, vz, b)
+        call("b2_compute_fb_fft", ptr(div_vb_fft), float(self.params.N), ptr(vz_fft), div_vb_fft.numel(), stream_ptr())
+        tendencies_fft.set_var("b_fft", div_vb_fft)
+
+
+class SimulNS2D(SimulBasePseudoSpectralB200):
+    """solvers/ns2d/solver.py:73-194."""
+
+    short_name = "ns2d"
+    ndim = 2
+    Operators = OperatorsPseudoSpectral2D
+    State = StateNS2D
+
+    def __init__(self, params, fused=None):
+        super().__init__(params, fused=fused)
+        self._fields_tmp = None
+
+    @property
+    def fields_tmp(self):
+        if self._fields_tmp is None:
+            self._fields_tmp = tuple(self.oper.create_arrayX() for _ in range(4))
+        return self._fields_tmp
+
+    def tendencies_nonlin(self, state_spect=None, old=None):
+        oper = self.oper
+        ifft_as_arg_destroy = oper.oper_fft.ifft_as_arg_destroy
+        if state_spect is None:
+            rot_fft = self.state.state_spect.get_var("rot_fft")
+            ux = self.state.state_phys.get_var("ux")
+            uy = self.state.state_phys.get_var("uy")
+        else:
+            rot_fft = state_spect.get_var("rot_fft")
+            ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
+            ux, uy = self.fields_tmp[0:2]
+            ifft_as_arg_destroy(ux_fft, ux)
+            ifft_as_arg_destroy(uy_fft, uy)
+        px_rot_fft, py_rot_fft = oper.gradfft_from_fft(rot_fft)
+        px_rot, py_rot = self.fields_tmp[2:4]
+        ifft_as_arg_destroy(px_rot_fft, px_rot)
+        ifft_as_arg_destroy(py_rot_fft, py_rot)
+        # compute_Frot (solver.py:34-38), result in px_rot's buffer
+        call("b2_compute_frot", ptr(ux), ptr(uy), ptr(px_rot), ptr(py_rot), float(self.params.beta),
+             ptr(px_rot), px_rot.numel(), stream_ptr())
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state.state_spect)
+        else:
+            tendencies_fft = old
+        Frot_fft = tendencies_fft.get_var("rot_fft")
+        oper.fft_as_arg(px_rot, Frot_fft)
+        oper.dealiasing(Frot_fft)
+        return tendencies_fft
+
+
+SIMUL_CLASSES = {"ns3d": SimulNS3D, "ns3d.strat": SimulNS3DStrat, "ns2d": SimulNS2D}
+
+
+def make_simul(solver, params, fused=None):
+    return SIMUL_CLASSES[solver](params, fused=fused)

@@ -1,0 +1,246 @@
+"""GPU branch of ``TimeSteppingPseudoSpectral`` (RK2 / RK4 with exact linear term).
+
+Host-side mirror of ``/root/reference/fluidsim/base/time_stepping/base.py:96-354`` (main loop,
+``one_time_step``, CFL time increment) and ``pseudo_spect.py:155-243,469-517,798-984`` (schemes).
+Two execution modes, same results to round-off:
+
+* **fused** (default when all sizes are powers of two in [8, 2048]): one call of the C ABI
+  ``b2_time_step`` per step -- per stage: first inverse pass with the curl computed on load,
+  y pass, fused x pass (c2r x6 -> v x omega -> r2c x3), forward y / z passes and ONE epilogue kernel
+  doing buoyancy coupling + Leray projection + dealiasing + the exact-linear RK update.
+* **unfused**: the reference's own sequence (``tendencies_nonlin`` + ``step_Euler`` /
+  ``rk4_step1-3`` / ``step_like_RK2``) executed with the operator-level kernels; works for any
+  grid size (odd, non power of two) and is what ``sim.tendencies_nonlin`` exposes.
+"""
+
+import signal
+from time import time
+from warnings import warn
+
+import torch
+
+from ._lib import SCHEME_IDS, call, ptr, stream_ptr
+from .setofvariables import SetOfVariables
+
+
+class ExactLinearCoefs:
+    """pseudo_spect.py:103-152 -- ``exact = exp(-dt sigma)``, ``exact2 = exp(-dt/2 sigma)``."""
+
+    def __init__(self, time_stepping):
+        self.time_stepping = time_stepping
+        sim = time_stepping.sim
+        self.sim = sim
+        oper = sim.oper
+        self.exact = torch.empty(oper.shapeK_loc, dtype=torch.float64, device=oper.device)
+        self.exact2 = torch.empty_like(self.exact)
+        self.dt_old = None
+        if sim.params.time_stepping.USE_CFL:
+            self.get_updated_coefs = self.get_updated_coefs_CLF
+        else:
+            self.compute(time_stepping.deltat)
+            self.get_updated_coefs = self.get_coefs
+
+    def compute(self, dt):
+        p = self.sim.params
+        call(
+            "b2_exact_coefs", self.sim.oper.plan.handle, p.nu_2, p.nu_4, p.nu_8, p.nu_m4, dt,
+            ptr(self.exact), ptr(self.exact2), stream_ptr(),
+        )
+        self.dt_old = dt
+
+    def get_updated_coefs_CLF(self):
+        dt = self.time_stepping.deltat
+        if self.dt_old != dt:
+            self.compute(dt)
+        return self.exact, self.exact2
+
+    def get_coefs(self):
+        return self.exact, self.exact2
+
+
+class TimeSteppingPseudoSpectralB200:
+    def __init__(self, sim, fused=None):
+        self.params = sim.params
+        self.sim = sim
+        self.it = 0
+        self.t = 0
+        self._stop_signal_received = False
+        self._has_to_stop = False
+        self.max_elapsed = None
+        try:
+            signal.signal(signal.SIGUSR2, self._handler_signals)
+        except (ValueError, AttributeError):
+            warn("Cannot handle signals - is multithreading on?")
+        self.fused = sim.oper.plan.is_fast if fused is None else bool(fused)
+        if self.fused and not sim.oper.plan.is_fast:
+            raise ValueError("fused time stepping needs power-of-two grid sizes in [8, 2048]")
+        self.init_from_params()
+
+    def _handler_signals(self, signal_number, stack):
+        print(f"signal {signal_number} received.")
+        self._stop_signal_received = True
+
+    # ---- init (pseudo_spect.py:173-224, base.py:246-304) --------------------------------------------
+    def init_from_params(self):
+        self._init_compute_time_step()
+        self._init_time_scheme()
+        self._exact_linear_coefs = None
+
+    @property
+    def exact_linear_coefs(self):
+        if self._exact_linear_coefs is None:
+            self._exact_linear_coefs = ExactLinearCoefs(self)
+        return self._exact_linear_coefs
+
+    def _init_compute_time_step(self):
+        params_ts = self.params.time_stepping
+        if params_ts.USE_CFL:
+            if params_ts.cfl_coef is not None:
+                self.CFL = params_ts.cfl_coef
+            elif any(params_ts.type_time_scheme.startswith(s) for s in ["RK2", "Euler"]):
+                self.CFL = 0.4
+            elif params_ts.type_time_scheme.startswith("RK4"):
+                self.CFL = 1.0
+            else:
+                raise ValueError("Problem name time_scheme")
+        self.deltat = params_ts.deltat0
+        self.deltat_max = params_ts.deltat_max
+        self._maxbuf = torch.zeros(1, dtype=torch.float64, device=self.sim.oper.device)
+
+    def _init_time_scheme(self):
+        type_time_scheme = self.params.time_stepping.type_time_scheme
+        if type_time_scheme == "RK2":
+            self._time_step_RK = self._time_step_RK2
+        elif type_time_scheme == "RK4":
+            self._time_step_RK = self._time_step_RK4
+        else:
+            raise ValueError(f'Problem name time_scheme ("{type_time_scheme}")')
+        self._scheme_id = SCHEME_IDS[type_time_scheme]
+        self._state_spect_tmp = None
+        self._state_spect_tmp1 = None
+
+    # ---- CFL (base.py:320-354) -----------------------------------------------------------------------
+    def _max_abs(self, x):
+        call("b2_max_abs", ptr(x), x.numel(), ptr(self._maxbuf), stream_ptr())
+        return float(self._maxbuf.item())
+
+    def compute_time_increment_CLF(self):
+        get_var = self.sim.state.get_var
+        oper = self.sim.oper
+        if self.sim.ndim == 3:
+            tmp = (
+                self._max_abs(get_var("vx")) / oper.deltax
+                + self._max_abs(get_var("vy")) / oper.deltay
+                + self._max_abs(get_var("vz")) / oper.deltaz
+            )
+        else:
+            tmp = self._max_abs(get_var("ux")) / oper.deltax + self._max_abs(get_var("uy")) / oper.deltay
+        self._compute_time_increment_CLF_from_tmp(tmp)
+
+    def _compute_time_increment_CLF_from_tmp(self, tmp):
+        deltat_CFL = self.CFL / tmp if tmp > 0 else self.deltat_max
+        maybe_new_dt = min(deltat_CFL, self.deltat_max)
+        normalize_diff = abs(self.deltat - maybe_new_dt) / maybe_new_dt
+        if normalize_diff > 0.02:
+            self.deltat = maybe_new_dt
+
+    # ---- main loop (base.py:144-244) ----------------------------------------------------------------
+    def start(self):
+        self.main_loop(print_begin=True, save_init_field=True)
+
+    def main_loop(self, print_begin=False, save_init_field=False):
+        params_stepping = self.params.time_stepping
+        if self.max_elapsed is not None:
+            self._time_should_stop = time() + self.max_elapsed
+        if params_stepping.USE_T_END:
+            while self.t < params_stepping.t_end and not self._has_to_stop:
+                self.one_time_step()
+        else:
+            while self.it < params_stepping.it_end and not self._has_to_stop:
+                self.one_time_step()
+
+    def is_simul_completed(self):
+        if self.params.time_stepping.USE_T_END:
+            return self.t >= self.params.time_stepping.t_end
+        return self.it >= self.params.time_stepping.it_end
+
+    def one_time_step(self):
+        if self.params.time_stepping.USE_CFL:
+            self.compute_time_increment_CLF()
+        if self.max_elapsed is not None and time() > self._time_should_stop:
+            self._has_to_stop = True
+        if self._stop_signal_received:
+            self._has_to_stop = True
+        self.one_time_step_computation()
+        self.t += self.deltat
+        self.it += 1
+
+    # ---- one step -----------------------------------------------------------------------------------
+    check_nan_period = 1
+
+    def one_time_step_computation(self):
+        """solvers/ns3d/time_stepping.py:8-20 (3-D) / pseudo_spect.py:236-243 (2-D)."""
+        sim = self.sim
+        state_spect = sim.state.state_spect
+        if self.fused:
+            sim._ensure_fused_buffers()
+            call(
+                "b2_time_step", sim.oper.plan.handle, self._scheme_id, float(self.deltat),
+                ptr(state_spect.tensor), stream_ptr(),
+            )
+        else:
+            self._time_step_RK()
+            if sim.ndim == 3:
+                sim.project_state_spect(state_spect)
+            sim.oper.dealiasing(state_spect)
+        sim.state.statephys_from_statespect()
+        if self.check_nan_period and (self.it + 1) % self.check_nan_period == 0:
+            call("b2_sum", ptr(state_spect.tensor), 2 * state_spect.tensor[0].numel(), ptr(self._maxbuf), stream_ptr())
+            if torch.isnan(self._maxbuf).item():
+                raise ValueError(f"nan at it = {self.it}, t = {self.t:.4f}")
+
+    # ---- unfused schemes (pseudo_spect.py:469-517, 798-984) -------------------------------------------
+    def _tmp_like_state(self, name):
+        buf = getattr(self, name)
+        if buf is None:
+            buf = SetOfVariables(like=self.sim.state.state_spect)
+            setattr(self, name, buf)
+        return buf
+
+    def _time_step_RK2(self):
+        dt = self.deltat
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        sim = self.sim
+        h = sim.oper.plan.handle
+        state_spect = sim.state.state_spect
+        nvar = state_spect.nvar
+        tendencies_0 = sim.tendencies_nonlin()
+        state_spect_12 = self._tmp_like_state("_state_spect_tmp")
+        call("b2_step_euler", h, ptr(state_spect.tensor), dt / 2, ptr(tendencies_0.tensor), ptr(diss2),
+             ptr(state_spect_12.tensor), nvar, stream_ptr())
+        tendencies_12 = sim.tendencies_nonlin(state_spect_12, old=tendencies_0)
+        call("b2_step_like_rk2", h, ptr(state_spect.tensor), dt, ptr(tendencies_12.tensor), ptr(diss),
+             ptr(diss2), nvar, stream_ptr())
+
+    def _time_step_RK4(self):
+        dt = self.deltat
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        sim = self.sim
+        h = sim.oper.plan.handle
+        state_spect = sim.state.state_spect
+        nvar = state_spect.nvar
+        S = ptr(state_spect.tensor)
+        tendencies_0 = sim.tendencies_nonlin()
+        state_spect_tmp = self._tmp_like_state("_state_spect_tmp")
+        state_spect_tmp1 = self._tmp_like_state("_state_spect_tmp1")
+        acc, tmp1 = ptr(state_spect_tmp.tensor), ptr(state_spect_tmp1.tensor)
+        # rk4_step0
+        call("b2_step_euler", h, S, dt / 6, ptr(tendencies_0.tensor), ptr(diss), acc, nvar, stream_ptr())
+        call("b2_step_euler", h, S, dt / 2, ptr(tendencies_0.tensor), ptr(diss2), tmp1, nvar, stream_ptr())
+        tendencies_1 = sim.tendencies_nonlin(state_spect_tmp1, old=tendencies_0)
+        call("b2_rk4_step1", h, S, acc, tmp1, ptr(tendencies_1.tensor), ptr(diss2), dt, nvar, stream_ptr())
+        tendencies_2 = sim.tendencies_nonlin(state_spect_tmp1, old=tendencies_1)
+        call("b2_rk4_step2", h, S, acc, tmp1, ptr(tendencies_2.tensor), ptr(diss), ptr(diss2), dt, nvar,
+             stream_ptr())
+        tendencies_3 = sim.tendencies_nonlin(state_spect_tmp1, old=tendencies_2)
+        call("b2_rk4_step3", h, S, acc, ptr(tendencies_3.tensor), dt, nvar, stream_ptr())

@@ -134,6 +134,13 @@ int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 long long b2_launch_count(void);
 
+/* ---- measurement hooks (bench.py roofline leg): per-kernel-class device time of the fused path,
+ * CUDA events recorded on the launching stream.  Classes: 0 first inverse pass (+curl prologue),
+ * 1 y inverse, 2 fused x pass, 3 y forward, 4 z forward, 5 RK / projection epilogue. */
+int b2_profile_enable(int on);
+int b2_profile_reset(void);
+int b2_profile_get(double* ms, long long* count, int ncat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,2 @@
+#!/bin/bash
+python -m pytest tests -x -q -m gpu 2>&1 | tail -40

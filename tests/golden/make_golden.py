@@ -1,0 +1,74 @@
+"""Generate golden vectors by running the REFERENCE's own hot-path code (build container only).
+
+The reference tree keeps no stored vectors for this path, so these
+fixtures are produced here by importing the unmodified reference modules from /root/reference
+through ``oracle.refshim`` (only the absent fluidfft layer is the numpy restatement
+``oracle.fluidfft_np``).  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Each ``.npz`` holds: the case parameters (json), the initial ``state_spect``, the dealiasing mask
+the reference used, ``state_spect`` after 1 and after ``nsteps`` reference steps, the reference's
+``tendencies_nonlin`` of the initial state, and scalar observables.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim, step_np  # noqa: E402
+
+CASES = {
+    # name: (solver, shape (nx, ny[, nz]), nsteps, params)
+    "ns3d_16x16x16_rk4": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),
+    "ns3d_32x16x8_rk2_f": ("ns3d", (32, 16, 8), 5, dict(nu_8=1e-8, deltat0=1e-2, type_time_scheme="RK2", f=0.7, Lx=6.0, Ly=4.0, Lz=3.0)),
+    "ns3d_16x12x8_rk4_odd": ("ns3d", (16, 12, 8), 3, dict(nu_4=2e-3, nu_8=1e-6, deltat0=2e-2, Lx=6.0)),
+    "ns3d_20x15x10_rk4_spherical": ("ns3d", (20, 15, 10), 3, dict(nu_2=5e-3, nu_m4=1e-3, deltat0=2e-2, truncation_shape="spherical")),
+    "strat_16x16x16_rk4": ("ns3d.strat", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2, N=2.0)),
+    "strat_16x8x32_rk2": ("ns3d.strat", (16, 8, 32), 4, dict(nu_4=1e-3, deltat0=1e-2, N=0.5, f=0.3, type_time_scheme="RK2")),
+    "ns2d_32x32_rk4": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
+    "ns2d_64x32_rk2_beta": ("ns2d", (64, 32), 5, dict(nu_2=1e-3, deltat0=1e-2, beta=0.4, type_time_scheme="RK2", Lx=8.0, Ly=8.0)),
+    "ns2d_24x15_rk4_odd": ("ns2d", (24, 15), 3, dict(nu_2=1e-3, deltat0=2e-2, Lx=8.0, Ly=8.0, truncation_shape="no_multiple_aliases")),
+}
+
+
+def main():
+    outdir = os.path.dirname(os.path.abspath(__file__))
+    for name, (solver, shape, nsteps, kw) in CASES.items():
+        nx, ny = shape[0], shape[1]
+        nz = shape[2] if len(shape) == 3 else None
+        # initial condition: the reference's noise recipe (restated in step_np.init_noise, which
+        # is itself checked against the reference in tests/test_oracle.py)
+        o = step_np.OracleSim(solver, nx, ny, nz, **kw)
+        o.init_noise()
+        s0 = np.array(o.state_spect)
+        params = refshim.make_params(solver, nx, ny, nz, **kw)
+        ref = refshim.RefSim(solver, params)
+        ref.set_state_spect(s0)
+        mask = np.array(ref.oper.where_dealiased)
+        tend0 = np.array(ref.sim.tendencies_nonlin())
+        states = []
+        for _ in range(nsteps):
+            states.append(ref.step())
+        e = step_np.OracleSim(solver, nx, ny, nz, **kw)
+        e.set_state_spect(states[-1])
+        np.savez_compressed(
+            os.path.join(outdir, name + ".npz"),
+            meta=json.dumps(dict(solver=solver, shape=shape, nsteps=nsteps, params=kw)),
+            state0=s0,
+            mask=mask,
+            tend0=tend0,
+            state1=states[0],
+            stateN=states[-1],
+            energyN=e.compute_energy(),
+            enstrophyN=e.compute_enstrophy(),
+        )
+        print(name, "ok", s0.shape)
+
+
+if __name__ == "__main__":
+    main()

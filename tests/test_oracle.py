@@ -1,0 +1,80 @@
+"""CPU tests: the numpy oracle against the committed golden vectors and (in the build container)
+against the reference's own modules executed through ``oracle.refshim``."""
+import numpy as np
+import pytest
+
+from helpers import golden_cases, load_golden, make_oracle, rel_err
+from oracle import refshim, step_np
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_oracle_matches_golden(name):
+    meta, z = load_golden(name)
+    o = make_oracle(meta)
+    assert np.array_equal(o.oper.where_dealiased, z["mask"])
+    o.set_state_spect(z["state0"])
+    tend = np.array(o.tendencies_nonlin())
+    assert rel_err(tend, z["tend0"]) < 1e-13
+    o.one_time_step()
+    assert rel_err(o.state_spect, z["state1"]) < 1e-13
+    for _ in range(meta["nsteps"] - 1):
+        o.one_time_step()
+    assert rel_err(o.state_spect, z["stateN"]) < 1e-12
+    assert abs(o.compute_energy() - float(z["energyN"])) <= 1e-12 * abs(float(z["energyN"]))
+
+
+def test_noise_init_is_deterministic_and_solenoidal():
+    o = step_np.OracleSim("ns3d", 16, 12, 8, nu_2=1e-2)
+    o.init_noise()
+    s = np.array(o.state_spect)
+    o2 = step_np.OracleSim("ns3d", 16, 12, 8, nu_2=1e-2)
+    o2.init_noise()
+    assert np.array_equal(s, np.array(o2.state_spect))
+    div = o.oper.divfft_from_vecfft(*s)
+    assert np.abs(div).max() < 1e-14
+    vmax = np.sqrt((np.array(o.state_phys) ** 2).sum(0)).max()
+    assert abs(vmax - 1.0) < 1e-12
+
+
+def test_nonlinear_term_conserves_energy():
+    """solvers/ns3d/test_solver.py:73-96 on the oracle."""
+    o = step_np.OracleSim("ns3d", 20, 15, 10, nu_2=0.0, coef_dealiasing=2 / 3)
+    o.init_noise()
+    T = np.array(o.tendencies_nonlin())
+    S = np.array(o.state_spect)
+    ratio = np.real(T.conj() * S)
+    tot = sum(o.oper.sum_wavenumbers(ratio[i]) for i in range(3))
+    tot_abs = sum(o.oper.sum_wavenumbers(np.abs(ratio[i])) for i in range(3))
+    assert abs(tot) / tot_abs < 1e-13
+
+
+def test_taylor_green_energy():
+    o = step_np.OracleSim("ns3d", 16, 16, 16, nu_2=1 / 1600.0)
+    o.init_taylor_green()
+    assert abs(o.compute_energy() - 0.125) < 1e-14
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize(
+    "solver,shape,kw",
+    [
+        ("ns3d", (16, 12, 8), dict(nu_2=0.01, deltat0=0.02)),
+        ("ns3d", (20, 15, 10), dict(nu_8=1e-4, deltat0=0.02, type_time_scheme="RK2", truncation_shape="spherical")),
+        ("ns3d.strat", (16, 12, 8), dict(nu_4=0.001, deltat0=0.02, N=2.0, f=0.5)),
+        ("ns2d", (32, 24), dict(nu_8=1e-6, deltat0=0.02, Lx=8, Ly=8)),
+        ("ns2d", (32, 24), dict(nu_2=1e-3, deltat0=0.02, beta=0.3, type_time_scheme="RK2")),
+    ],
+)
+def test_oracle_equals_reference_code(solver, shape, kw):
+    """The restatement must reproduce the reference's own Python bit for bit."""
+    nx, ny = shape[0], shape[1]
+    nz = shape[2] if len(shape) == 3 else None
+    ref = refshim.RefSim(solver, refshim.make_params(solver, nx, ny, nz, **kw))
+    o = step_np.OracleSim(solver, nx, ny, nz, **kw)
+    o.init_noise()
+    ref.set_state_spect(np.array(o.state_spect))
+    assert np.array_equal(ref.oper.where_dealiased, o.oper.where_dealiased)
+    for _ in range(3):
+        a = ref.step()
+        b = np.array(o.one_time_step())
+        assert np.array_equal(a, b)

@@ -1,0 +1,269 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the
+numpy oracle and the committed golden vectors made from the reference's own code.
+
+Tolerances (BASELINE.json north_star): float64 state within 1e-10 relative per step; energy /
+enstrophy / spectra within 1e-8 after 100 steps.  Observed differences are round-off (1e-15 ..
+1e-13); the asserts below use 1e-11 per step so that regressions are caught early.
+"""
+import numpy as np
+import pytest
+import scipy.fft as sfft
+
+from helpers import golden_cases, load_golden, make_gpu_sim, make_oracle, rel_err, set_state
+
+pytestmark = pytest.mark.gpu
+
+TOL_STEP = 1e-11  # north_star tolerance is 1e-10 relative per step
+TOL_OBS = 1e-8
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+# ------------------------------------------------------------------ transforms
+@pytest.mark.parametrize(
+    "shape",
+    [(8, 8, 8), (16, 32, 64), (128, 64, 32), (4, 11, 16), (10, 15, 20), (9, 8, 7), (16, 16, 6), (256, 256, 256)],
+)
+def test_fft3d_matches_scipy(shape):
+    torch = _torch()
+    from fluidsim_b200.fft import FFT3DWithB200
+
+    o = FFT3DWithB200(*shape)
+    rng = np.random.default_rng(1)
+    x = rng.random(shape) - 0.5
+    xd = torch.from_numpy(x).cuda()
+    k = o.fft(xd)
+    kr = sfft.rfftn(x) / np.prod(shape)
+    assert rel_err(k.cpu().numpy(), kr) < 1e-14
+    x2 = o.ifft(k)
+    assert float((x2 - xd).abs().max()) < 1e-14
+    # ifft_as_arg must leave its input intact; the destroy variant may not
+    k0 = k.clone()
+    out = o.create_arrayX()
+    o.ifft_as_arg(k, out)
+    assert torch.equal(k, k0)
+    o.ifft_as_arg_destroy(k, out)
+    assert float((out - xd).abs().max()) < 1e-14
+    # host (numpy) calling convention of the reference
+    kh = np.empty(o.get_shapeK_loc(), dtype=np.complex128)
+    o.fft_as_arg(x, kh)
+    assert rel_err(kh, kr) < 1e-14
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (64, 1024), (2048, 512), (15, 24), (11, 9)])
+def test_fft2d_matches_scipy(shape):
+    torch = _torch()
+    from fluidsim_b200.fft import FFT2DWithB200
+
+    o = FFT2DWithB200(*shape)
+    rng = np.random.default_rng(2)
+    x = rng.random(shape) - 0.5
+    xd = torch.from_numpy(x).cuda()
+    k = o.fft(xd)
+    assert rel_err(k.cpu().numpy(), sfft.rfft2(x) / np.prod(shape)) < 1e-14
+    assert float((o.ifft(k) - xd).abs().max()) < 1e-14
+
+
+def test_c2r_ignores_imaginary_part_of_self_conjugate_modes():
+    """FFTW c2r semantics: Im of the kx=0 / Nyquist self-conjugate modes does not matter."""
+    torch = _torch()
+    from fluidsim_b200.fft import FFT3DWithB200
+
+    shape = (8, 8, 16)
+    o = FFT3DWithB200(*shape)
+    rng = np.random.default_rng(3)
+    k = rng.random(o.get_shapeK_loc()) + 1j * rng.random(o.get_shapeK_loc())
+    ref = sfft.irfftn(k, s=shape) * np.prod(shape)
+    out = o.ifft(torch.from_numpy(k).cuda()).cpu().numpy()
+    assert rel_err(out, ref) < 1e-13
+
+
+# ------------------------------------------------------------------ operators
+def test_operators3d_against_oracle():
+    torch = _torch()
+    meta = dict(solver="ns3d", shape=(16, 12, 10), params=dict(Lx=6.0, Ly=5.0, Lz=3.0, nu_2=1e-2))
+    o = make_oracle(meta)
+    sim = make_gpu_sim(meta, fused=False)
+    oper = sim.oper
+    assert np.array_equal(oper.where_dealiased.cpu().numpy(), o.oper.where_dealiased)
+    assert np.allclose(oper.K2.cpu().numpy(), o.oper.K2, rtol=1e-15)
+    rng = np.random.default_rng(4)
+    shapeK = o.oper.shapeK_loc
+    v = [rng.random(shapeK) + 1j * rng.random(shapeK) for _ in range(3)]
+    vd = [torch.from_numpy(a).cuda() for a in v]
+    rot = oper.rotfft_from_vecfft(*vd)
+    rot_o = o.oper.rotfft_from_vecfft(*v)
+    for a, b in zip(rot, rot_o):
+        assert rel_err(a.cpu().numpy(), b) < 1e-15
+    assert rel_err(oper.divfft_from_vecfft(*vd).cpu().numpy(), o.oper.divfft_from_vecfft(*v)) < 1e-15
+    vp = [a.copy() for a in v]
+    o.oper.project_perpk3d(*vp)
+    vpd = [a.clone() for a in vd]
+    oper.project_perpk3d(*vpd)
+    for a, b in zip(vpd, vp):
+        assert rel_err(a.cpu().numpy(), b) < 1e-14
+    # projection is idempotent and kills the divergence (test_operators3d.py:53-180)
+    assert float(oper.divfft_from_vecfft(*vpd).abs().max()) < 1e-13
+    # vector product writes into b
+    shapeX = o.oper.shapeX_loc
+    a3 = [rng.random(shapeX) for _ in range(3)]
+    b3 = [rng.random(shapeX) for _ in range(3)]
+    from fluidsim_b200.operators import vector_product
+
+    ad = [torch.from_numpy(x).cuda() for x in a3]
+    bd = [torch.from_numpy(x).cuda() for x in b3]
+    r = vector_product(*ad, *bd)
+    assert r[0] is bd[0]
+    ref = np.cross(np.stack(a3, -1), np.stack(b3, -1))
+    for i in range(3):
+        assert rel_err(bd[i].cpu().numpy(), ref[..., i]) < 1e-15
+    # energy reduction
+    e = oper.compute_energy_from_K(vd[0])
+    assert abs(e - o.oper.compute_energy_from_K(v[0])) < 1e-12 * abs(e)
+
+
+def test_bad_inputs_raise():
+    from fluidsim_b200.solvers import SimulNS3D
+
+    p = SimulNS3D.create_default_params()
+    p.oper.nx = p.oper.ny = p.oper.nz = 8
+    p.time_stepping.type_time_scheme = "RK3"
+    with pytest.raises(ValueError):
+        SimulNS3D(p)
+    p.time_stepping.type_time_scheme = "RK4"
+    p.oper.type_fft = "fft3d.with_pyfftw"
+    with pytest.raises(ValueError):
+        SimulNS3D(p)
+    p.oper.type_fft = "fft3d.with_b200"
+    p.oper.truncation_shape = "banana"
+    with pytest.raises(ValueError):
+        SimulNS3D(p)
+
+
+# ------------------------------------------------------------------ golden vectors (reference code)
+@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("fused", [False, True])
+def test_step_matches_reference_golden(name, fused):
+    meta, z = load_golden(name)
+    sim_probe = make_gpu_sim(meta, fused=False, mask=z["mask"])
+    if fused and not sim_probe.oper.plan.is_fast:
+        pytest.skip("fused path needs power-of-two sizes")
+    sim = make_gpu_sim(meta, fused=fused, mask=z["mask"])
+    set_state(sim, z["state0"])
+    tend = sim.tendencies_nonlin_fused() if fused else sim.tendencies_nonlin()
+    assert rel_err(tend.numpy(), z["tend0"]) < TOL_STEP
+    sim.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), z["state1"]) < TOL_STEP
+    for _ in range(meta["nsteps"] - 1):
+        sim.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), z["stateN"]) < 10 * TOL_STEP
+    if meta["solver"] != "ns2d":
+        e = sim.state.compute_energy_spect()
+        assert abs(e - float(z["energyN"])) < TOL_OBS * abs(float(z["energyN"]))
+        assert sim.state.check_energy_equal_phys_spect()
+
+
+# ------------------------------------------------------------------ BASELINE configs 1 and 2
+def _run_both(meta, nsteps, init):
+    o = make_oracle(meta)
+    getattr(o, init)()
+    sim = make_gpu_sim(meta, fused=True, mask=o.oper.where_dealiased)
+    set_state(sim, np.array(o.state_spect))
+    worst = 0.0
+    for _ in range(nsteps):
+        o.one_time_step()
+        sim.time_stepping.one_time_step()
+        worst = max(worst, rel_err(sim.state.state_spect.numpy(), np.array(o.state_spect)))
+    return o, sim, worst
+
+
+def test_config1_ns2d_256_noise_rk4_100_steps():
+    """BASELINE config 1: ns2d 256^2 random init RK4 (fluidsim-bench protocol: L=8, nu_8=1)."""
+    meta = dict(solver="ns2d", shape=(256, 256), params=dict(nu_8=1.0, deltat0=1e-3, Lx=8.0, Ly=8.0))
+    o, sim, worst = _run_both(meta, 100, "init_noise")
+    assert worst < 1e-10
+    e_o, z_o = o.compute_energy(), o.compute_enstrophy()
+    assert abs(sim.state.compute_energy_spect() - e_o) < TOL_OBS * e_o
+    z_gpu = 0.5 * sim.oper.oper_fft.sum_wavenumbers_abs2(sim.state.state_spect.tensor)
+    assert abs(z_gpu - z_o) < TOL_OBS * z_o
+
+
+def test_config2_ns3d_128_taylor_green_rk4():
+    """BASELINE config 2: ns3d 128^3 Taylor-Green RK4 (nu_2 = 1/1600, dt = 1e-2): per-step state
+    parity, then energy / spectrum / spatial means."""
+    meta = dict(solver="ns3d", shape=(128, 128, 128), params=dict(nu_2=1 / 1600.0, deltat0=1e-2))
+    nsteps = 20  # the oracle needs ~1 s per step on the box's host cores
+    o, sim, worst = _run_both(meta, nsteps, "init_taylor_green")
+    assert worst < 1e-10
+    e_o = o.compute_energy()
+    assert abs(sim.state.compute_energy_spect() - e_o) < TOL_OBS * e_o
+    t = sim.state.state_spect.tensor
+    e_fft = 0.5 * (t[0].abs() ** 2 + t[1].abs() ** 2 + t[2].abs() ** 2)
+    spec_gpu = sim.oper.compute_3dspectrum(e_fft)
+    spec_o = o.compute_spectrum3d()
+    assert np.abs(spec_gpu - spec_o).max() < TOL_OBS * spec_o.max()
+    # spatial means of the physical fields (vx^2 ...), from the lazily computed state_phys
+    phys = sim.state.state_phys.numpy()
+    for i in range(3):
+        m_o = float(np.mean(np.array(o.state_phys[i]) ** 2))
+        assert abs(float(np.mean(phys[i] ** 2)) - m_o) < TOL_OBS * max(m_o, 1e-3)
+
+
+def test_ns3d_strat_64_noise_rk4():
+    meta = dict(solver="ns3d.strat", shape=(64, 64, 64), params=dict(nu_8=1e-10, deltat0=5e-3, N=1.0))
+    o, sim, worst = _run_both(meta, 10, "init_noise")
+    assert worst < 1e-10
+    assert abs(sim.state.compute_energy_spect() - o.compute_energy()) < TOL_OBS * o.compute_energy()
+
+
+# ------------------------------------------------------------------ invariants at larger sizes
+def test_nonlinear_term_conserves_energy_256():
+    """solvers/ns3d/test_solver.py:73-96 at a size the oracle would not finish quickly."""
+    torch = _torch()
+    meta = dict(solver="ns3d", shape=(256, 256, 256), params=dict(nu_2=0.0, deltat0=1e-3))
+    sim = make_gpu_sim(meta, fused=True)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapeX = sim.oper.shapeX_loc
+    v = [sim.oper.fft(torch.rand(shapeX, dtype=torch.float64, device="cuda", generator=g) - 0.5) for _ in range(3)]
+    sim.oper.project_perpk3d(*v)
+    sim.oper.dealiasing(*v)
+    sim.state.init_statespect_from(vx_fft=v[0], vy_fft=v[1], vz_fft=v[2])
+    T = sim.tendencies_nonlin_fused().tensor
+    S = sim.state.state_spect.tensor
+    ratio = (T.conj() * S).real
+    tot = sum(sim.oper.sum_wavenumbers(ratio[i]) for i in range(3))
+    tot_abs = sum(sim.oper.sum_wavenumbers(ratio[i].abs()) for i in range(3))
+    assert abs(tot) / tot_abs < 1e-13
+    # tendencies are divergence free and dealiased
+    assert float(sim.oper.divfft_from_vecfft(T[0], T[1], T[2]).abs().max()) < 1e-12
+    assert float(T[:, sim.oper.where_dealiased.bool()].abs().max()) == 0.0
+
+
+def test_cfl_time_increment_matches_oracle():
+    meta = dict(solver="ns3d", shape=(32, 32, 32), params=dict(nu_2=1e-2, deltat0=0.2))
+    o = make_oracle(meta)
+    o.init_noise()
+    sim = make_gpu_sim(meta, fused=True, mask=o.oper.where_dealiased)
+    sim.params.time_stepping.USE_CFL = True
+    sim.time_stepping.init_from_params()
+    set_state(sim, np.array(o.state_spect))
+    for _ in range(3):
+        dt_o = o.compute_time_increment_CFL(cfl=1.0, deltat_max=0.2)
+        o.one_time_step()
+        sim.time_stepping.one_time_step()
+        assert abs(sim.time_stepping.deltat - dt_o) < 1e-12 * dt_o
+        assert rel_err(sim.state.state_spect.numpy(), np.array(o.state_spect)) < 1e-10
+
+
+def test_nan_raises_value_error():
+    torch = _torch()
+    meta = dict(solver="ns3d", shape=(16, 16, 16), params=dict(nu_2=1e-2, deltat0=1e-2))
+    sim = make_gpu_sim(meta, fused=True)
+    sim.state.state_spect.tensor.fill_(0)
+    sim.state.state_spect.tensor[0, 1, 1, 1] = float("nan")
+    with pytest.raises(ValueError, match="nan at it"):
+        sim.time_stepping.one_time_step()
