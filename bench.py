@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the pseudo-spectral RK4 step (BASELINE.json metric: ns3d RK4 steps/s and
+grid-pts*steps/s), own arm (CUDA, libb200spectral) and reference arm (CPU, oracle port).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 512] [--solver ns3d]
+
+Prints ONE JSON line (rank 0).  A "step" is one full RK4 time step (4 evaluations of the nonlinear
+term = 36 3-D FFTs + epilogues) of the named solver on a synthetic noise field; protocol restated
+from fluidsim-bench (/root/reference/fluidsim/util/console/util.py:147-215): L = 2 pi,
+coef_dealiasing = 2/3, nu_8 = 1, deltat0 = 1e-4, USE_CFL = False, outputs off.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ns3d_rk4_grid_points_steps_per_s"
+UNIT = "grid-pts*steps/s"
+
+# algorithmic HBM bytes, in field passes F = 16*n0*n1*(n2/2+1) bytes
+STEP_PASSES = {("ns3d", "RK4"): 195, ("ns3d.strat", "RK4"): 282, ("ns2d", "RK4"): 57, ("ns3d", "RK2"): 90}
+# per-launch field passes of each kernel class of the fused path (ns3d): read + written fields
+CLASS_NAMES = ["first_inverse_pass_curl", "y_inverse", "x_fused_c2r_cross_r2c", "y_forward", "z_forward",
+               "rk_project_dealias_epilogue"]
+CLASS_PASSES = {
+    "ns3d": [3 + 6, 6 + 6, 6 + 3, 3 + 3, 3 + 3, (12 + 15 + 15 + 9) / 4.0 + 1 / 16.0],
+    "ns3d.strat": [4 + 7, 7 + 7, 7 + 6, 6 + 6, 6 + 6, (18 + 22 + 22 + 14) / 4.0 + 1 / 16.0],
+    "ns2d": [1 + 4, 0, 4 + 1, 1 + 1, 0, (4 + 5 + 5 + 3) / 4.0 + 1 / 16.0],
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=512, help="grid size per axis (power of two)")
+    ap.add_argument("--solver", default="ns3d", choices=["ns3d", "ns3d.strat", "ns2d"])
+    ap.add_argument("--scheme", default="RK4", choices=["RK4", "RK2"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=128, help="grid size of the bounded CPU sample")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(device_index)],
+                stdout=self.tmp, stderr=subprocess.DEVNULL,
+            )
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_run(solver, scheme, n, nsteps, warmup, max_seconds=25.0):
+    """Oracle port (reference Python restated + pocketfft, all host threads) on an n^3 sample."""
+    from oracle import step_np
+
+    cores = len(os.sched_getaffinity(0))
+    kw = dict(nu_8=1.0, deltat0=1e-4, type_time_scheme=scheme)
+    if solver == "ns2d":
+        o = step_np.OracleSim(solver, n, n, None, Lx=8.0, Ly=8.0, **kw)
+    else:
+        o = step_np.OracleSim(solver, n, n, n, **kw)
+    o.init_noise()
+    for _ in range(warmup):
+        o.one_time_step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < nsteps:
+        o.one_time_step()
+        done += 1
+        if time.perf_counter() - t0 > max_seconds:
+            break
+    dt = (time.perf_counter() - t0) / done
+    pts = n**o.ndim
+    return dict(ms_per_step=dt * 1e3, steps=done, value=pts / dt, cores=cores, n=n)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_n
+    r = cpu_run(args.solver, args.scheme, n, args.steps, min(args.warmup, 1), max_seconds=150.0)
+    sample = (f"{args.solver} {n}^{3 if args.solver != 'ns2d' else 2} {args.scheme} noise init, {r['steps']} steps "
+              f"(bounded sample of the {args.n}^3 workload; value is per grid point so sizes compare)")
+    line = {
+        "impl": "reference",
+        "metric": METRIC if args.solver == "ns3d" else f"{args.solver}_{args.scheme.lower()}_grid_points_steps_per_s",
+        "value": r["value"],
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": r["steps"],
+        "warmup": min(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.solver} {args.n}^3 {args.scheme} float64 (fluidsim-bench protocol)",
+                   "cpu_sample_n": n},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                         "sample": sample + "; reference-Python restated in numpy + scipy pocketfft "
+                                            "(fluidfft/FFTW/MPI are not installable offline)"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- own arm
+def make_sim(args, torch):
+    from fluidsim_b200.solvers import SIMUL_CLASSES
+
+    cls = SIMUL_CLASSES[args.solver]
+    p = cls.create_default_params()
+    n = args.n
+    p.oper.nx = p.oper.ny = n
+    if args.solver != "ns2d":
+        p.oper.nz = n
+    else:
+        p.oper.Lx = p.oper.Ly = 8.0
+    p.oper.coef_dealiasing = 2.0 / 3
+    p.nu_8 = 1.0
+    p.time_stepping.USE_CFL = False
+    p.time_stepping.USE_T_END = False
+    p.time_stepping.deltat0 = 1e-4
+    p.time_stepping.type_time_scheme = args.scheme
+    sim = cls(p, fused=True)
+    sim.time_stepping.check_nan_period = 0  # checked once after the timed region
+    init_noise_on_device(sim, torch)
+    return sim
+
+
+def init_noise_on_device(sim, torch, seed=42):
+    """Noise recipe of solvers/ns3d/init_fields.py:153-196 with a device RNG (the NumPy recipe
+    cannot allocate the large grids on the host): uniform noise -> project -> dealias -> low-pass
+    tanh(k0 - K) -> rescale to velo_max = 1."""
+    oper = sim.oper
+    g = torch.Generator(device=oper.device).manual_seed(seed)
+    nvar = sim.state.state_spect.nvar
+    S = sim.state.state_spect.tensor
+    x = oper.create_arrayX()
+    for i in range(nvar):
+        x.uniform_(-0.5, 0.5, generator=g)
+        oper.fft_as_arg(x, S[i])
+    S[(slice(None),) + (0,) * sim.ndim] = 0.0
+    if sim.ndim == 3:
+        oper.project_perpk3d(S[0], S[1], S[2])
+    oper.dealiasing(sim.state.state_spect)
+    k0 = 2 * 3.141592653589793 / (oper.Lx / 4.0)
+    chunk = max(1, S.shape[1] // 16)
+    kx2 = (oper._k2d if sim.ndim == 3 else oper._kxd) ** 2
+    for a in range(0, S.shape[1], chunk):
+        if sim.ndim == 3:
+            K = torch.sqrt(kx2[None, None, :] + oper._k1d[None, :, None] ** 2 + oper._k0d[a:a + chunk, None, None] ** 2)
+        else:
+            K = torch.sqrt(kx2[None, :] + oper._kyd[a:a + chunk, None] ** 2)
+        S[:, a:a + chunk] *= (1.0 + torch.tanh(2 * 3.141592653589793 * (k0 - K) / k0)) / 2.0
+    # normalise with the spectral energy (max |v| would need 3 more physical fields at 1024^3)
+    e = sim.state.compute_energy_spect() if sim.ndim == 3 else None
+    if e:
+        S *= (0.5 / e) ** 0.5 * 0.3
+    sim.state.mark_spect_modified()
+
+
+def own_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (own arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fluidsim_b200 import _lib
+
+    hbm_peak, peak_src = peaks()
+    sim = make_sim(args, torch)
+    ts = sim.time_stepping
+    S = sim.state.state_spect.tensor
+    npts = float(args.n) ** sim.ndim
+    F = 16.0 * S[0].numel()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ts.one_time_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ts.one_time_step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * npts / (ms_per_step * 1e-3)
+    if not bool(torch.isfinite(S.real.sum()).item()):
+        raise RuntimeError("state became non finite during the benchmark")
+
+    # ---- per-kernel-class timing (CUDA events on the launching stream inside the library)
+    roofline = None
+    classes = {}
+    if rank == 0:
+        import ctypes as C
+
+        _lib.lib.b2_profile_reset()
+        _lib.lib.b2_profile_enable(1)
+        nprof = max(2, min(args.steps, 5))
+        for _ in range(nprof):
+            ts.one_time_step()
+        msarr = (C.c_double * 6)()
+        cnt = (C.c_longlong * 6)()
+        _lib.lib.b2_profile_get(msarr, cnt, 6)
+        _lib.lib.b2_profile_enable(0)
+        passes = CLASS_PASSES[args.solver]
+        tot = sum(msarr)
+        best = None
+        for i, name in enumerate(CLASS_NAMES):
+            if cnt[i] == 0:
+                continue
+            avg = msarr[i] / cnt[i]
+            ach = passes[i] * F / (avg * 1e-3) / 1e9
+            classes[name] = {"launches_per_step": cnt[i] / nprof, "avg_ms": avg, "share": msarr[i] / tot,
+                             "alg_GBps": ach, "frac": ach / hbm_peak}
+            if best is None or msarr[i] > msarr[best]:
+                best = i
+        bname = CLASS_NAMES[best]
+        roofline = {"bound": "hbm", "kernel": bname, "achieved": classes[bname]["alg_GBps"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": classes[bname]["frac"], "traffic": None,
+                    "peak_source": peak_src,
+                    "alg_bytes_per_launch": passes[best] * F}
+    barrier()
+
+    # ---- end to end through the public API with HOST buffers (state in pinned host memory)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        host = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+        host.copy_(S)
+        torch.cuda.synchronize()
+        ksteps = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            S.copy_(host, non_blocking=True)
+            sim.state.mark_spect_modified()
+            ts.one_time_step()
+            host.copy_(S, non_blocking=True)
+            torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ksteps
+        nbytes = S.numel() * 16
+        e2e = {"value": npts / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "ms_per_step": dt * 1e3, "steps": ksteps}
+        del host
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_run(args.solver, args.scheme, args.cpu_n, 10, 1, max_seconds=20.0)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                        "sample": f"{args.solver} {r['n']}^{sim.ndim} {args.scheme}, {r['steps']} steps of the numpy/"
+                                  f"pocketfft oracle port, {r['ms_per_step']:.0f} ms/step"}
+
+    if rank == 0:
+        step_passes = STEP_PASSES.get((args.solver, args.scheme))
+        step_alg = step_passes * F / world if step_passes else None
+        line = {
+            "metric": METRIC if args.solver == "ns3d" else f"{args.solver}_{args.scheme.lower()}_grid_points_steps_per_s",
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "steps_per_s": 1e3 / ms_per_step,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{args.solver} {args.n}^{sim.ndim} {args.scheme} float64, noise init, nu_8=1, dt=1e-4, "
+                            "USE_CFL=False (fluidsim-bench protocol; forcing off)",
+                "n": args.n,
+                "state_bytes": S.numel() * 16,
+                "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
+                "parallelism": "single GPU" if world == 1 else f"replicas x{world}",
+            },
+            "roofline": roofline,
+            "step_roofline": {
+                "model_field_passes": step_passes,
+                "alg_bytes_per_step": step_alg,
+                "achieved_GBps": step_alg / (ms_per_step * 1e-3) / 1e9 if step_alg else None,
+                "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / hbm_peak if step_alg else None,
+            },
+            "kernel_classes": classes,
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        own_arm(args)
+
+
+if __name__ == "__main__":
+    main()
