@@ -68,6 +68,7 @@ SIGNATURES = {
     "b2_profile_enable": [_i],
     "b2_profile_reset": [],
     "b2_profile_get": [C.POINTER(_d), C.POINTER(_ll), _i],
+    "b2_dev_strided_pass": [_p, _i, _i, _p, _p, _i, _p],
 }
 _RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": _ll}
 

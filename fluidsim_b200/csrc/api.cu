@@ -919,3 +919,18 @@ extern "C" int b2_time_step(b2_plan* p, int scheme, double dt, double* S_, void*
     }
     return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
 }
+
+// ------------------------------------------------------------------------------- development hooks
+// raw strided pass over nf contiguous K fields (micro-benchmarks / tuning only)
+extern "C" int b2_dev_strided_pass(b2_plan* p, int axis, int dir, const double* in, double* out, int nf,
+                                   void* stream) {
+    if (nf < 1 || nf > 8) return b2i_set_error("b2_dev_strided_pass: nf out of range");
+    const cplx* i_[8];
+    cplx* o_[8];
+    const long long fs = p->fsize();
+    for (int f = 0; f < nf; ++f) {
+        i_[f] = (const cplx*)in + f * fs;
+        o_[f] = (cplx*)out + f * fs;
+    }
+    return b2i_strided_plain(p, axis, dir, i_, o_, nf, 1.0, (cudaStream_t)stream);
+}

@@ -20,6 +20,7 @@ struct Geom {
     long long es;   // stride (elements) between successive points of a line
     long long os;   // stride (elements) between outer batches
     long long cs;   // stride between columns (1 for the fast path)
+    int nf;         // number of fields handled by the launch
 };
 
 #define B2_MAXF 8
@@ -56,9 +57,11 @@ __global__ void __launch_bounds__(TK*(N / E))
     double* sim = b2_smem + PS;
     const int c = threadIdx.x % TK;
     const int t = threadIdx.x / TK;
-    const int col = blockIdx.x * TK + c;
+    // field is the fastest-varying block coordinate: the CTAs that (re-)read the same input tile
+    // for different output fields (curl prologue) run at the same time and share it through L2
+    const int field = blockIdx.x % g.nf;
+    const int col = (blockIdx.x / g.nf) * TK + c;
     const int outer = blockIdx.y;
-    const int field = blockIdx.z;
     const bool active = col < g.ncols;
     const long long base = (long long)outer * g.os + col;
     cplx x[E];
@@ -230,6 +233,54 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 #pragma unroll
         for (int m = 0; m < E; ++m) x[m] = park[(o * E + m) * T + t];
         r2c_line<N, E>(x, op.out[o] + loff, sre, sim, t, twN, SyncBlock(), scale, active);
+    }
+}
+
+
+// Field-parallel variant (used when T = (N/2)/E >= 32): one CTA per line, NI thread groups of T
+// threads.  Group g does the c2r of input field g; after one CTA barrier groups o < NO form output
+// o of the pointwise product from the parked physical lines and do its r2c.  Compared with the
+// single-group kernel this multiplies the number of resident warps per line by NI, which is what
+// the latency hiding of this pass needs (see profiles/).
+// Op additionally provides: __device__ double point1(int o, const double* u) const.
+template <int N, int E, class Op>
+__global__ void __launch_bounds__(Op::NI*((N / 2) / E))
+    xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
+    extern __shared__ double b2_smem[];
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int NI = Op::NI, NO = Op::NO;
+    static_assert(T % 32 == 0, "field-parallel x pass needs whole warps per group");
+    const int g = threadIdx.x / T, t = threadIdx.x % T;
+    const long long line = blockIdx.x;
+    cplx* park = reinterpret_cast<cplx*>(b2_smem);            // [NI][E][T] complex
+    double* sre = b2_smem + 2 * (size_t)NI * M + (size_t)g * 2 * PS;  // per-group exchange planes
+    double* sim = sre + PS;
+    const long long loff = line * (M + 1);
+    cplx x[E];
+    if constexpr (T == 32) {
+        c2r_line<N, E>(x, op.in[g] + loff, sre, sim, t, twN, SyncWarp());
+    } else {
+        c2r_line<N, E>(x, op.in[g] + loff, sre, sim, t, twN, SyncNamed<T>{g + 1});
+    }
+#pragma unroll
+    for (int m = 0; m < E; ++m) park[(g * E + m) * T + t] = x[m];
+    __syncthreads();
+    if (g >= NO) return;
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        double ue[NI], uo[NI];
+#pragma unroll
+        for (int f = 0; f < NI; ++f) {
+            const cplx v = park[(f * E + m) * T + t];
+            ue[f] = v.x;
+            uo[f] = v.y;
+        }
+        x[m] = make_double2(op.point1(g, ue), op.point1(g, uo));
+    }
+    if constexpr (T == 32) {
+        r2c_line<N, E>(x, op.out[g] + loff, sre, sim, t, twN, SyncWarp(), scale, true);
+    } else {
+        r2c_line<N, E>(x, op.out[g] + loff, sre, sim, t, twN, SyncNamed<T>{g + 1}, scale, true);
     }
 }
 

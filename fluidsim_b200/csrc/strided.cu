@@ -1,5 +1,7 @@
 // Strided-axis (y / z) FFT passes and the fused first inverse pass (curl / ns2d prologue on load).
 #include "internal.h"
+#include <stdlib.h>
+
 #include "passes.cuh"
 
 // per-size configuration of the strided pass: E points per thread, TK columns per CTA tile
@@ -14,9 +16,18 @@ template <> struct SCfg<32>   { static constexpr int E = 4,  TK = 16; };
 template <> struct SCfg<16>   { static constexpr int E = 4,  TK = 16; };
 template <> struct SCfg<8>    { static constexpr int E = 2,  TK = 16; };
 
-template <int N, int DIR, class L, class S>
-static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
-    constexpr int E = SCfg<N>::E, TK = SCfg<N>::TK;
+// tuning knob (development): B2_SVAR=<variant> selects alternative (E, TK) for N = 512 / 1024
+static int strided_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2_SVAR");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+template <int N, int E, int TK, int DIR, class L, class S>
+static int launch_strided_cfg(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
     constexpr size_t smem = 2 * (size_t)PlaneSize<N>::value * TK * sizeof(double);
     auto kern = fft_strided_kernel<N, E, TK, DIR, L, S>;
     static bool attr_done = false;
@@ -25,7 +36,8 @@ static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStre
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    dim3 grid((g.ncols + TK - 1) / TK, g.nouter, nf);
+    g.nf = nf;
+    dim3 grid(((g.ncols + TK - 1) / TK) * nf, g.nouter, 1);
     kern<<<grid, TK*(N / E), smem, s>>>(g, ld, st, tw);
     B2_LAUNCH_CHECK("fft_strided_kernel");
     return 0;
@@ -59,6 +71,27 @@ static int launch_generic(int N, Geom g, int nf, L ld, S st, const cplx* tw, cud
     return 0;
 }
 
+template <int N, int DIR, class L, class S>
+static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
+    if constexpr (N == 1024) {
+        switch (strided_variant()) {
+            case 1: return launch_strided_cfg<N, 8, 4, DIR>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
+            case 3: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
+            case 4: return launch_strided_cfg<N, 16, 2, DIR>(g, nf, ld, st, tw, s);
+        }
+    }
+    if constexpr (N == 512) {
+        switch (strided_variant()) {
+            case 1: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
+            case 3: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
+            case 4: return launch_strided_cfg<N, 4, 4, DIR>(g, nf, ld, st, tw, s);
+        }
+    }
+    return launch_strided_cfg<N, SCfg<N>::E, SCfg<N>::TK, DIR>(g, nf, ld, st, tw, s);
+}
+
 template <int DIR, class L, class S>
 static int launch_strided(bool fast, int N, Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
     if (fast) {
@@ -86,6 +119,7 @@ static Geom geom_for_axis(const b2_plan* p, int axis) {
         g.os = (long long)p->n1 * p->nk;
     }
     g.cs = 1;
+    g.nf = 1;
     return g;
 }
 

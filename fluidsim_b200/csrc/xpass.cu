@@ -37,6 +37,11 @@ struct OpNS3D {
         r[1] = u[2] * u[3] - u[0] * u[5];
         r[2] = u[0] * u[4] - u[1] * u[3];
     }
+    B2_DEVINL double point1(int o, const double* u) const {
+        if (o == 0) return u[1] * u[5] - u[2] * u[4];
+        if (o == 1) return u[2] * u[3] - u[0] * u[5];
+        return u[0] * u[4] - u[1] * u[3];
+    }
 };
 // ns3d.strat: f = v x omega and v*b (div_vb_fft_from_vb, strat/solver.py:206)
 struct OpStrat {
@@ -51,6 +56,12 @@ struct OpStrat {
         r[4] = u[1] * u[6];
         r[5] = u[2] * u[6];
     }
+    B2_DEVINL double point1(int o, const double* u) const {
+        if (o == 0) return u[1] * u[5] - u[2] * u[4];
+        if (o == 1) return u[2] * u[3] - u[0] * u[5];
+        if (o == 2) return u[0] * u[4] - u[1] * u[3];
+        return u[o - 3] * u[6];
+    }
 };
 // ns2d: Frot = -ux d_x rot - uy (d_y rot + beta)  (compute_Frot, solvers/ns2d/solver.py:34-38)
 struct OpNS2D {
@@ -60,6 +71,9 @@ struct OpNS2D {
     double beta;
     B2_DEVINL void point(const double* u, double* r) const {
         r[0] = beta == 0.0 ? -u[0] * u[2] - u[1] * u[3] : -u[0] * u[2] - u[1] * (u[3] + beta);
+    }
+    B2_DEVINL double point1(int o, const double* u) const {
+        return beta == 0.0 ? -u[0] * u[2] - u[1] * u[3] : -u[0] * u[2] - u[1] * (u[3] + beta);
     }
 };
 
@@ -89,8 +103,27 @@ static int launch_r2c_n(const double* X, cplx* K, long long nlines, const cplx* 
 }
 
 template <int N, class Op>
+static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, cudaStream_t s) {
+    constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
+    constexpr size_t smem = (2 * (size_t)Op::NI * M + 2 * (size_t)Op::NI * PlaneSize<M>::value) * sizeof(double);
+    auto kern = xpass_fused_fp_kernel<N, E, Op>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    kern<<<(unsigned)nlines, Op::NI * T, smem, s>>>(op, nlines, tw, scale);
+    B2_LAUNCH_CHECK("xpass_fused_fp_kernel");
+    return 0;
+}
+
+template <int N, class Op>
 static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
+    constexpr size_t smem_fp =
+        (2 * (size_t)Op::NI * M + 2 * (size_t)Op::NI * PlaneSize<M>::value) * sizeof(double);
+    if constexpr (T % 32 == 0 && smem_fp <= 227 * 1024) return launch_fused_fp_n<N>(op, nlines, tw, scale, s);
     constexpr size_t per_ls = (2 * (size_t)PlaneSize<M>::value + 2 * (size_t)Op::NI * M) * sizeof(double);
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
@@ -171,6 +204,7 @@ static int launch_generic_x(int N, long long nlines, L ld, S st, const cplx* tw,
     g.es = 0;
     g.os = 0;
     g.cs = 0;
+    g.nf = 1;
     dim3 grid((unsigned)((nlines + TK - 1) / TK), 1, 1);
     kern<<<grid, 256, smem, s>>>(N, TK, g, ld, st, tw, factorize(N));
     B2_LAUNCH_CHECK("fft_generic_kernel(x)");

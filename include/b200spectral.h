@@ -140,6 +140,9 @@ long long b2_launch_count(void);
 int b2_profile_enable(int on);
 int b2_profile_reset(void);
 int b2_profile_get(double* ms, long long* count, int ncat);
+/* development hook: one raw strided FFT pass (axis 0 = z, 1 = y; dir -1 fwd / +1 inv) over nf
+ * contiguous K fields; used by the tuning micro-benchmarks only */
+int b2_dev_strided_pass(b2_plan* p, int axis, int dir, const double* in, double* out, int nf, void* stream);
 
 #ifdef __cplusplus
 }
