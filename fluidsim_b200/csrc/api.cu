@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -73,6 +74,9 @@ static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** ou
 extern "C" int b2_plan_create(b2_plan** out, int ndim, int n0, int n1, int n2, double L0, double L1,
                               double L2) {
     if (!out) return b2i_set_error("b2_plan_create: out is NULL");
+    if (const char* gr = getenv("B2_L2GRAN")) {  // tuning knob: L2 fetch granularity hint (32/64/128 B)
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));
+    }
     if (ndim != 2 && ndim != 3) return b2i_set_error("b2_plan_create: ndim must be 2 or 3");
     b2_plan* p = new b2_plan();
     memset(p, 0, sizeof(*p));
@@ -173,16 +177,23 @@ static KGrid kgrid(const b2_plan* p) { return KGrid{p->k0, p->k1, p->kx, p->n0, 
 static inline unsigned nrows(const b2_plan* p) { return (unsigned)((long long)p->n0 * p->n1); }
 #define B2_ROW_THREADS 128
 
+// omega = i k x v  (rotfft_from_vecfft_outin); `f` is added to omega_z at k = 0
+// (_modif_omegafft_with_f, /root/reference/fluidsim/solvers/ns3d/solver.py:176-178)
+B2_DEVINL void curl3(double Kx, double Ky, double Kz, cplx a, cplx b, cplx c, cplx& rx, cplx& ry, cplx& rz) {
+    rx = make_double2(-(Ky * c.y - Kz * b.y), Ky * c.x - Kz * b.x);
+    ry = make_double2(-(Kz * a.y - Kx * c.y), Kz * a.x - Kx * c.x);
+    rz = make_double2(-(Kx * b.y - Ky * a.y), Kx * b.x - Ky * a.x);
+}
 __global__ void rot_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* vz, cplx* rx, cplx* ry,
-                           cplx* rz) {
+                           cplx* rz, double f) {
     B2_ROW_SETUP
     for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
-        const cplx a = vx[i], b = vy[i], c = vz[i];
-        rx[i] = make_double2(-(Ky * c.y - Kz * b.y), Ky * c.x - Kz * b.x);
-        ry[i] = make_double2(-(Kz * a.y - Kx * c.y), Kz * a.x - Kx * c.x);
-        rz[i] = make_double2(-(Kx * b.y - Ky * a.y), Kx * b.x - Ky * a.x);
+        cplx ox, oy, oz;
+        curl3(Kx, Ky, Kz, vx[i], vy[i], vz[i], ox, oy, oz);
+        if (row == 0 && ikx == 0) oz.x += f;
+        rx[i] = ox; ry[i] = oy; rz[i] = oz;
     }
 }
 
@@ -310,7 +321,7 @@ __global__ void rot2d_kernel(KGrid g, const cplx* ux, const cplx* uy, cplx* rot)
 extern "C" int b2_rotfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const double* vz,
                                      double* rx, double* ry, double* rz, void* stream) {
     rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(
-        kgrid(p), (const cplx*)vx, (const cplx*)vy, (const cplx*)vz, (cplx*)rx, (cplx*)ry, (cplx*)rz);
+        kgrid(p), (const cplx*)vx, (const cplx*)vy, (const cplx*)vz, (cplx*)rx, (cplx*)ry, (cplx*)rz, 0.0);
     B2_LAUNCH_CHECK("rot_kernel");
     return 0;
 }
@@ -689,8 +700,10 @@ enum { M_TEND = 0, M_RK4_0, M_RK4_1, M_RK4_2, M_RK4_3, M_RK2_0, M_RK2_1 };
 struct RKArgs {
     KGrid g;
     Visc visc;
-    const cplx* W;    // raw FFT output: nwork_out fields, stride fsize
+    cplx* W;          // raw FFT output: nwork_out fields, stride fsize; W[3..5] receive the
+                      // vorticity of the next stage input
     const cplx* Sin;  // stage input (strat coupling terms)
+    double fcor;      // Coriolis parameter added to omega_z(k=0) (0 if params.f is None)
     cplx* S;          // state (nvar fields)
     cplx* A;          // accumulator
     cplx* B;          // next stage input
@@ -746,7 +759,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
             if (MODE != M_RK4_1 && MODE != M_RK2_0) E = exp(-dt * fd);
             if (MODE != M_RK4_3) E2 = exp(-dt / 2 * fd);
         }
-        cplx Sn[NV];
+        cplx Sn[NV];  // new state (last stage) or next stage input B (other stages)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             const long long j = v * a.fsize + i;
@@ -755,21 +768,21 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
                 const cplx s = a.S[j];
                 const double c6 = dt / 6, c2 = dt / 2;
                 a.A[j] = make_double2((s.x + c6 * t.x) * E, (s.y + c6 * t.y) * E);
-                a.B[j] = make_double2((s.x + c2 * t.x) * E2, (s.y + c2 * t.y) * E2);
+                Sn[v] = make_double2((s.x + c2 * t.x) * E2, (s.y + c2 * t.y) * E2);
             } else if (MODE == M_RK4_1) {
                 const cplx s = a.S[j];
                 cplx ac = a.A[j];
                 const double c = dt / 3 * E2, h = dt / 2;
                 ac.x += c * t.x; ac.y += c * t.y;
                 a.A[j] = ac;
-                a.B[j] = make_double2(s.x * E2 + h * t.x, s.y * E2 + h * t.y);
+                Sn[v] = make_double2(s.x * E2 + h * t.x, s.y * E2 + h * t.y);
             } else if (MODE == M_RK4_2) {
                 const cplx s = a.S[j];
                 cplx ac = a.A[j];
                 const double c = dt / 3 * E2, c2 = dt * E2;
                 ac.x += c * t.x; ac.y += c * t.y;
                 a.A[j] = ac;
-                a.B[j] = make_double2(s.x * E + c2 * t.x, s.y * E + c2 * t.y);
+                Sn[v] = make_double2(s.x * E + c2 * t.x, s.y * E + c2 * t.y);
             } else if (MODE == M_RK4_3) {
                 const cplx ac = a.A[j];
                 const double c = dt / 6;
@@ -777,11 +790,24 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
             } else if (MODE == M_RK2_0) {
                 const cplx s = a.S[j];
                 const double h = dt / 2;
-                a.B[j] = make_double2((s.x + h * t.x) * E2, (s.y + h * t.y) * E2);
+                Sn[v] = make_double2((s.x + h * t.x) * E2, (s.y + h * t.y) * E2);
             } else {  // M_RK2_1
                 const cplx s = a.S[j];
                 const double c2 = dt * E2;
                 Sn[v] = make_double2(s.x * E + c2 * t.x, s.y * E + c2 * t.y);
+            }
+        }
+        if (MODE == M_RK4_0 || MODE == M_RK4_1 || MODE == M_RK4_2 || MODE == M_RK2_0) {
+            // next stage input, and (3-D) its vorticity for the next first inverse pass
+#pragma unroll
+            for (int v = 0; v < NV; ++v) a.B[v * a.fsize + i] = Sn[v];
+            if (SOLVER != B2_SOLVER_NS2D) {
+                cplx ox, oy, oz;
+                curl3(Kx, Ky, Kz, Sn[0], Sn[1], Sn[2], ox, oy, oz);
+                if (origin) oz.x += a.fcor;
+                a.W[3 * a.fsize + i] = ox;
+                a.W[4 * a.fsize + i] = oy;
+                a.W[5 * a.fsize + i] = oz;
             }
         }
         if (MODE == M_RK4_3 || MODE == M_RK2_1) {
@@ -819,7 +845,7 @@ static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s
 }
 
 // raw nonlinear term of stage input `Sin` into work[0..nout-1] (scaled FFT, not yet projected)
-static int nonlinear_raw(b2_plan* p, const cplx* Sin, cudaStream_t s) {
+static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream_t s) {
     int nwork, nvar;
     if (b2_work_fields(p, p->solver, &nwork, &nvar)) return -1;
     const long long fs = p->fsize();
@@ -831,6 +857,12 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, cudaStream_t s) {
     const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
     const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
     int e;
+    if (need_curl && p->solver != B2_SOLVER_NS2D) {
+        ProfScope ps(PC_RK, s);
+        rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, s>>>(kgrid(p), in[0], in[1], in[2], W[3], W[4], W[5],
+                                                      p->has_f ? p->f : 0.0);
+        B2_LAUNCH_CHECK("rot_kernel");
+    }
     {
         ProfScope ps(PC_FIRST_INV, s);
         if ((e = b2i_first_inverse_pass(p, in, W, s))) return e;
@@ -878,6 +910,7 @@ static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     a.fsize = p->fsize();
     a.dt = dt;
     a.N2 = p->N * p->N;
+    a.fcor = p->has_f ? p->f : 0.0;
     return a;
 }
 
@@ -886,7 +919,7 @@ extern "C" int b2_tendencies(b2_plan* p, const double* S_in, double* T_out, void
     int e;
     if ((e = check_fused_ready(p, false))) return e;
     const cplx* Sin = (const cplx*)S_in;
-    if ((e = nonlinear_raw(p, Sin, s))) return e;
+    if ((e = nonlinear_raw(p, Sin, true, s))) return e;
     RKArgs a = rk_args(p, Sin, nullptr, 0.0);
     a.Tout = (cplx*)T_out;
     return launch_rk_stage(p, M_TEND, a, s);
@@ -901,7 +934,7 @@ extern "C" int b2_time_step(b2_plan* p, int scheme, double dt, double* S_, void*
         const int modes[4] = {M_RK4_0, M_RK4_1, M_RK4_2, M_RK4_3};
         for (int st = 0; st < 4; ++st) {
             const cplx* Sin = st == 0 ? S : p->stage;
-            if ((e = nonlinear_raw(p, Sin, s))) return e;
+            if ((e = nonlinear_raw(p, Sin, st == 0, s))) return e;
             RKArgs a = rk_args(p, Sin, S, dt);
             if ((e = launch_rk_stage(p, modes[st], a, s))) return e;
         }
@@ -911,7 +944,7 @@ extern "C" int b2_time_step(b2_plan* p, int scheme, double dt, double* S_, void*
         const int modes[2] = {M_RK2_0, M_RK2_1};
         for (int st = 0; st < 2; ++st) {
             const cplx* Sin = st == 0 ? S : p->stage;
-            if ((e = nonlinear_raw(p, Sin, s))) return e;
+            if ((e = nonlinear_raw(p, Sin, st == 0, s))) return e;
             RKArgs a = rk_args(p, Sin, S, dt);
             if ((e = launch_rk_stage(p, modes[st], a, s))) return e;
         }

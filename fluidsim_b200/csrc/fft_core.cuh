@@ -139,12 +139,20 @@ struct Bfly<16, DIR> {
 };
 
 // ---------------------------------------------------------------------------------------
-// shared-memory exchange plane addressing
-//   logical index w in [0, N) -> padded index w + (w >> 4); TK interleaved columns.
-B2_DEVINL int b2_pad(int w) { return w + (w >> 4); }
-template <int N>
-struct PlaneSize {
-    static constexpr int value = N + (N >> 4) + 1;  // doubles per column per plane
+// shared-memory exchange plane: complex128 elements (128-bit LDS/STS), TK interleaved columns,
+// element index = pad(w) * TK + c.  A quarter-warp (8 lanes x 16 B) must cover all 32 banks:
+//   TK >= 8 : the 8 lanes are 8 columns of one row -> never a conflict, no padding
+//   TK == 4 : two rows per quarter-warp -> pad so that rows r apart (r = radix) differ by an odd count
+//   TK <= 2 : lanes run along the line -> pad so that strides 8 and 16 map to distinct 16-byte groups
+template <int TK>
+B2_DEVINL int b2_pad(int w) {
+    if (TK >= 8) return w;
+    if (TK == 4) return w + (w >> 4);
+    return w + (w >> 3) + (w >> 6);
+}
+template <int N, int TK>
+struct PlaneSize {  // complex elements per column
+    static constexpr int value = TK >= 8 ? N : (TK == 4 ? N + (N >> 4) + 1 : N + (N >> 3) + (N >> 6) + 2);
 };
 
 struct SyncBlock {
@@ -163,11 +171,32 @@ struct SyncNamed {
     B2_DEVINL void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 };
 
+// powers w[m] = w1^m, m = 1..r-1, by binary products (depth <= 4 multiplications)
+template <int r>
+B2_DEVINL void twiddle_powers(cplx w1, cplx* w) {
+    w[1] = w1;
+    if (r > 2) w[2] = cmul(w1, w1);
+    if (r > 3) w[3] = cmul(w[2], w1);
+    if (r > 4) {
+        w[4] = cmul(w[2], w[2]);
+        w[5] = cmul(w[4], w1);
+        w[6] = cmul(w[4], w[2]);
+        w[7] = cmul(w[4], w[3]);
+    }
+    if (r > 8) {
+        w[8] = cmul(w[4], w[4]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) w[8 + k] = cmul(w[8], w[k]);
+    }
+}
+
 // Stockham stages.  TWS = stride in the twiddle table (table holds exp(-2 pi i k / (N*TWS))).
+// Twiddles: one table load (w^1) per butterfly, higher powers by multiplication -- the table
+// gathers of a per-element lookup saturate the L1/LSU pipe (profiles/README.md).
 template <int N, int E, int DIR, int TK, int TWS, int Ns, class Sync>
 struct FftStages {
-    static B2_DEVINL void run(cplx (&x)[E], double* __restrict__ sre, double* __restrict__ sim,
-                              int t, int c, const cplx* __restrict__ tw, Sync sync) {
+    static B2_DEVINL void run(cplx (&x)[E], cplx* __restrict__ plane, int t, int c,
+                              const cplx* __restrict__ tw, Sync sync) {
         constexpr int T = N / E;
         constexpr int Rem = N / Ns;
         constexpr int r = Rem >= E ? E : Rem;
@@ -179,44 +208,36 @@ struct FftStages {
             for (int m = 0; m < r; ++m) v[m] = x[q + m * Q];
             if (Ns > 1) {
                 const int jm = (t + q * T) & (Ns - 1);
+                cplx w1 = __ldg(tw + (size_t)jm * (TWS * (N / (Ns * r))));
+                if (DIR > 0) w1.y = -w1.y;
+                cplx w[r > 1 ? r : 2];
+                twiddle_powers<r>(w1, w);
 #pragma unroll
-                for (int m = 1; m < r; ++m) {
-                    cplx w = __ldg(tw + (size_t)(jm * m) * (TWS * (N / (Ns * r))));
-                    if (DIR > 0) w.y = -w.y;
-                    v[m] = cmul(v[m], w);
-                }
+                for (int m = 1; m < r; ++m) v[m] = cmul(v[m], w[m]);
             }
             Bfly<r, DIR>::run(v);
 #pragma unroll
             for (int m = 0; m < r; ++m) x[q + m * Q] = v[m];
         }
         if constexpr (Ns * r < N) {
-            sync();  // WAR on the planes (previous exchange / previous line)
+            sync();  // WAR on the plane (previous exchange / previous line)
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 const int j = t + q * T;
                 const int base = (j / Ns) * (Ns * r) + (j & (Ns - 1));
 #pragma unroll
-                for (int m = 0; m < r; ++m) {
-                    const int wp = b2_pad(base + m * Ns) * TK + c;
-                    sre[wp] = x[q + m * Q].x;
-                    sim[wp] = x[q + m * Q].y;
-                }
+                for (int m = 0; m < r; ++m) plane[b2_pad<TK>(base + m * Ns) * TK + c] = x[q + m * Q];
             }
             sync();
 #pragma unroll
-            for (int m = 0; m < E; ++m) {
-                const int pp = b2_pad(t + m * T) * TK + c;
-                x[m] = make_double2(sre[pp], sim[pp]);
-            }
-            FftStages<N, E, DIR, TK, TWS, Ns * r, Sync>::run(x, sre, sim, t, c, tw, sync);
+            for (int m = 0; m < E; ++m) x[m] = plane[b2_pad<TK>(t + m * T) * TK + c];
+            FftStages<N, E, DIR, TK, TWS, Ns * r, Sync>::run(x, plane, t, c, tw, sync);
         }
     }
 };
 
 // x[m] holds in[t + m*T] on entry and out[t + m*T] on exit (unnormalised).
 template <int N, int E, int DIR, int TK, int TWS, class Sync>
-B2_DEVINL void fft_line(cplx (&x)[E], double* sre, double* sim, int t, int c,
-                        const cplx* __restrict__ tw, Sync sync) {
-    FftStages<N, E, DIR, TK, TWS, 1, Sync>::run(x, sre, sim, t, c, tw, sync);
+B2_DEVINL void fft_line(cplx (&x)[E], cplx* plane, int t, int c, const cplx* __restrict__ tw, Sync sync) {
+    FftStages<N, E, DIR, TK, TWS, 1, Sync>::run(x, plane, t, c, tw, sync);
 }

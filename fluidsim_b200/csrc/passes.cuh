@@ -52,9 +52,7 @@ __global__ void __launch_bounds__(TK*(N / E))
     fft_strided_kernel(Geom g, LoadOp ld, StoreOp st, const cplx* __restrict__ tw) {
     extern __shared__ double b2_smem[];
     constexpr int T = N / E;
-    constexpr int PS = PlaneSize<N>::value * TK;
-    double* sre = b2_smem;
-    double* sim = b2_smem + PS;
+    cplx* plane = reinterpret_cast<cplx*>(b2_smem);
     const int c = threadIdx.x % TK;
     const int t = threadIdx.x / TK;
     // field is the fastest-varying block coordinate: the CTAs that (re-)read the same input tile
@@ -70,7 +68,7 @@ __global__ void __launch_bounds__(TK*(N / E))
         const int i = t + m * T;
         x[m] = active ? ld(field, base + (long long)i * g.es, i, col, outer) : make_double2(0.0, 0.0);
     }
-    fft_line<N, E, DIR, TK, 1>(x, sre, sim, t, c, tw, SyncBlock());
+    fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
     if (active) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
@@ -80,11 +78,22 @@ __global__ void __launch_bounds__(TK*(N / E))
     }
 }
 
+
+// ------------------------------------------------------------------------------- input ops
+// InOp interface (shared by the fast and the generic kernels):
+//     const cplx* ptr(int field, long long off, int i, int col, int outer) const  -- source address
+//     cplx xf(int field, cplx v, int i, int col, int outer) const                 -- value transform
+struct PlainIn {
+    const cplx* in[B2_MAXF];
+    B2_DEVINL const cplx* ptr(int f, long long off, int i, int col, int outer) const { return in[f] + off; }
+    B2_DEVINL cplx xf(int f, cplx v, int i, int col, int outer) const { return v; }
+};
+
 // ------------------------------------------------------------------------------- x pass pieces
 // c2r along a contiguous line of N reals (M = N/2 complex FFT).  On exit x[m] = (u[2n], u[2n+1]),
 // n = t + m*T.  Unnormalised (FFTW c2r convention).  Imaginary parts of k=0 and k=N/2 are ignored.
 template <int N, int E, class Sync>
-B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, double* sre, double* sim, int t,
+B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, cplx* plane, int t,
                         const cplx* __restrict__ twN, Sync sync) {
     constexpr int M = N / 2, T = M / E;
 #pragma unroll
@@ -103,22 +112,18 @@ B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, double* sre, d
             x[m] = make_double2(s.x - e.y, s.y + e.x);  // s + i e
         }
     }
-    fft_line<M, E, +1, 1, 2>(x, sre, sim, t, 0, twN, sync);
+    fft_line<M, E, +1, 1, 2>(x, plane, t, 0, twN, sync);
 }
 
 // r2c: x[m] = (u[2n], u[2n+1]) on entry; writes K[0..M] scaled by `scale`.
 template <int N, int E, class Sync>
-B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, double* sre, double* sim, int t,
+B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
                         const cplx* __restrict__ twN, Sync sync, double scale, bool do_store) {
     constexpr int M = N / 2, T = M / E;
-    fft_line<M, E, -1, 1, 2>(x, sre, sim, t, 0, twN, sync);
+    fft_line<M, E, -1, 1, 2>(x, plane, t, 0, twN, sync);
     sync();
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        const int p = b2_pad(t + m * T);
-        sre[p] = x[m].x;
-        sim[p] = x[m].y;
-    }
+    for (int m = 0; m < E; ++m) plane[b2_pad<1>(t + m * T)] = x[m];
     sync();
     const double hs = 0.5 * scale;
 #pragma unroll
@@ -130,8 +135,7 @@ B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, double* sre, double*
                 K[M] = make_double2((x[m].x - x[m].y) * scale, 0.0);
             }
         } else {
-            const int p = b2_pad(M - k);
-            const cplx zc = make_double2(sre[p], -sim[p]);  // conj(Z[M-k])
+            const cplx zc = cconj(plane[b2_pad<1>(M - k)]);  // conj(Z[M-k])
             const cplx s = cadd(x[m], zc);
             const cplx d = csub(x[m], zc);
             const cplx w = __ldg(twN + k);
@@ -152,15 +156,14 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     xpass_c2r_kernel(const cplx* __restrict__ K, double* __restrict__ X, long long nlines,
                      const cplx* __restrict__ twN) {
     extern __shared__ double b2_smem[];
-    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     const int ls = threadIdx.x / T, t = threadIdx.x % T;
     long long line = (long long)blockIdx.x * LPB + ls;
     const bool active = line < nlines;
     if (!active) line = nlines - 1;
-    double* sre = b2_smem + (size_t)ls * 2 * PS;
-    double* sim = sre + PS;
+    cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PS;
     cplx x[E];
-    c2r_line<N, E>(x, K + line * (M + 1), sre, sim, t, twN, SyncBlock());
+    c2r_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock());
     if (active) {
         double2* out = reinterpret_cast<double2*>(X + line * N);
 #pragma unroll
@@ -174,18 +177,17 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     xpass_r2c_kernel(const double* __restrict__ X, cplx* __restrict__ K, long long nlines,
                      const cplx* __restrict__ twN, double scale) {
     extern __shared__ double b2_smem[];
-    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     const int ls = threadIdx.x / T, t = threadIdx.x % T;
     long long line = (long long)blockIdx.x * LPB + ls;
     const bool active = line < nlines;
     if (!active) line = nlines - 1;
-    double* sre = b2_smem + (size_t)ls * 2 * PS;
-    double* sim = sre + PS;
+    cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PS;
     cplx x[E];
     const double2* in = reinterpret_cast<const double2*>(X + line * N);
 #pragma unroll
     for (int m = 0; m < E; ++m) x[m] = in[t + m * T];
-    r2c_line<N, E>(x, K + line * (M + 1), sre, sim, t, twN, SyncBlock(), scale, active);
+    r2c_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock(), scale, active);
 }
 
 // fused: NI spectral lines -> c2r -> pointwise Op -> r2c -> NO spectral lines.
@@ -196,21 +198,20 @@ template <int N, int E, int LPB, class Op>
 __global__ void __launch_bounds__(LPB*((N / 2) / E))
     xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
     extern __shared__ double b2_smem[];
-    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
-    constexpr int PER_LS = 2 * PS + 2 * NI * M;  // doubles per line-set
+    constexpr int PER_LS = PS + NI * M;  // complex elements per line-set
     const int ls = threadIdx.x / T, t = threadIdx.x % T;
     long long line = (long long)blockIdx.x * LPB + ls;
     const bool active = line < nlines;
     if (!active) line = nlines - 1;
-    double* sre = b2_smem + (size_t)ls * PER_LS;
-    double* sim = sre + PS;
-    cplx* park = reinterpret_cast<cplx*>(sre + 2 * PS);
+    cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PER_LS;
+    cplx* park = plane + PS;
     const long long loff = line * (M + 1);
     cplx x[E];
 #pragma unroll 1
     for (int f = 0; f < NI; ++f) {
-        c2r_line<N, E>(x, op.in[f] + loff, sre, sim, t, twN, SyncBlock());
+        c2r_line<N, E>(x, op.in[f] + loff, plane, t, twN, SyncBlock());
 #pragma unroll
         for (int m = 0; m < E; ++m) park[(f * E + m) * T + t] = x[m];
     }
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     for (int o = 0; o < NO; ++o) {
 #pragma unroll
         for (int m = 0; m < E; ++m) x[m] = park[(o * E + m) * T + t];
-        r2c_line<N, E>(x, op.out[o] + loff, sre, sim, t, twN, SyncBlock(), scale, active);
+        r2c_line<N, E>(x, op.out[o] + loff, plane, t, twN, SyncBlock(), scale, active);
     }
 }
 
@@ -247,20 +248,19 @@ template <int N, int E, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
     extern __shared__ double b2_smem[];
-    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M>::value;
+    constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
     static_assert(T % 32 == 0, "field-parallel x pass needs whole warps per group");
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const long long line = blockIdx.x;
-    cplx* park = reinterpret_cast<cplx*>(b2_smem);            // [NI][E][T] complex
-    double* sre = b2_smem + 2 * (size_t)NI * M + (size_t)g * 2 * PS;  // per-group exchange planes
-    double* sim = sre + PS;
+    cplx* park = reinterpret_cast<cplx*>(b2_smem);    // [NI][E][T] complex
+    cplx* plane = park + (size_t)NI * M + (size_t)g * PS;  // per-group exchange plane
     const long long loff = line * (M + 1);
     cplx x[E];
     if constexpr (T == 32) {
-        c2r_line<N, E>(x, op.in[g] + loff, sre, sim, t, twN, SyncWarp());
+        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp());
     } else {
-        c2r_line<N, E>(x, op.in[g] + loff, sre, sim, t, twN, SyncNamed<T>{g + 1});
+        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1});
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) park[(g * E + m) * T + t] = x[m];
@@ -278,9 +278,9 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
         x[m] = make_double2(op.point1(g, ue), op.point1(g, uo));
     }
     if constexpr (T == 32) {
-        r2c_line<N, E>(x, op.out[g] + loff, sre, sim, t, twN, SyncWarp(), scale, true);
+        r2c_line<N, E>(x, op.out[g] + loff, plane, t, twN, SyncWarp(), scale, true);
     } else {
-        r2c_line<N, E>(x, op.out[g] + loff, sre, sim, t, twN, SyncNamed<T>{g + 1}, scale, true);
+        r2c_line<N, E>(x, op.out[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, scale, true);
     }
 }
 

@@ -8,7 +8,7 @@
 template <int N> struct SCfg;
 template <> struct SCfg<2048> { static constexpr int E = 16, TK = 4; };
 template <> struct SCfg<1024> { static constexpr int E = 16, TK = 4; };
-template <> struct SCfg<512>  { static constexpr int E = 8,  TK = 4; };
+template <> struct SCfg<512>  { static constexpr int E = 16, TK = 8; };
 template <> struct SCfg<256>  { static constexpr int E = 8,  TK = 8; };
 template <> struct SCfg<128>  { static constexpr int E = 8,  TK = 8; };
 template <> struct SCfg<64>   { static constexpr int E = 8,  TK = 16; };
@@ -28,7 +28,7 @@ static int strided_variant() {
 
 template <int N, int E, int TK, int DIR, class L, class S>
 static int launch_strided_cfg(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
-    constexpr size_t smem = 2 * (size_t)PlaneSize<N>::value * TK * sizeof(double);
+    constexpr size_t smem = (size_t)PlaneSize<N, TK>::value * TK * sizeof(cplx);
     auto kern = fft_strided_kernel<N, E, TK, DIR, L, S>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -71,29 +71,41 @@ static int launch_generic(int N, Geom g, int nf, L ld, S st, const cplx* tw, cud
     return 0;
 }
 
+// adapter: InOp -> LoadOp for the small-size / generic kernels
+template <class In>
+struct LoadFromIn {
+    In in;
+    B2_DEVINL cplx operator()(int f, long long off, int i, int col, int outer) const {
+        return in.xf(f, *in.ptr(f, off, i, col, outer), i, col, outer);
+    }
+};
+
 template <int N, int DIR, class L, class S>
 static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
     if constexpr (N == 1024) {
+        // measured (profiles/r1_tuning.md): the plane-strided z pass wants 128-byte row segments
+        // (TK = 8, one 512-thread CTA per SM), the y pass prefers two 256-thread CTAs (TK = 4)
+        const bool zlike = g.nouter == 1;
         switch (strided_variant()) {
-            case 1: return launch_strided_cfg<N, 8, 4, DIR>(g, nf, ld, st, tw, s);
-            case 2: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
-            case 3: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
-            case 4: return launch_strided_cfg<N, 16, 2, DIR>(g, nf, ld, st, tw, s);
+            case 1: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
         }
+        if (zlike) return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
+        return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
     }
     if constexpr (N == 512) {
         switch (strided_variant()) {
-            case 1: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
-            case 2: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
-            case 3: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
-            case 4: return launch_strided_cfg<N, 4, 4, DIR>(g, nf, ld, st, tw, s);
+            case 1: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
+            case 3: return launch_strided_cfg<N, 8, 4, DIR>(g, nf, ld, st, tw, s);
         }
     }
     return launch_strided_cfg<N, SCfg<N>::E, SCfg<N>::TK, DIR>(g, nf, ld, st, tw, s);
 }
 
-template <int DIR, class L, class S>
-static int launch_strided(bool fast, int N, Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
+template <int DIR, class In, class S>
+static int launch_strided(bool fast, int N, Geom g, int nf, In in, S st, const cplx* tw, cudaStream_t s) {
+    LoadFromIn<In> ld{in};
     if (fast) {
         switch (N) {
 #define B2_CASE(n) case n: return launch_strided_n<n, DIR>(g, nf, ld, st, tw, s);
@@ -131,7 +143,7 @@ int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx
     const int N = axis == 0 ? p->n0 : p->n1;
     const bool fast = axis == 0 ? p->fast0 : p->fast1;
     const cplx* tw = axis == 0 ? p->tw0 : p->tw1;
-    PlainLoad ld;
+    PlainIn ld;
     for (int f = 0; f < nf; ++f) ld.in[f] = in[f];
     if (scale == 1.0) {
         PlainStore st;
@@ -146,72 +158,35 @@ int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx
                    : launch_strided<+1>(fast, N, g, nf, ld, st, tw, s);
 }
 
-// ------------------------------------------------------------------------------- fused prologues
-// ns3d / ns3d.strat: rotfft_from_vecfft_outin (+ Coriolis f on the k=0 mode) computed on load.
-// /root/reference/fluidsim/solvers/ns3d/solver.py:199-204, strat/solver.py:154-160.
-template <int AXIS>
-struct CurlLoad {
-    const cplx* in[4];
-    const double *k0, *k1, *kx;
-    int nk;
-    int has_f;
-    double f;
-    B2_DEVINL cplx operator()(int fld, long long off, int i, int col, int outer) const {
-        if (fld < 3) return in[fld][off];
-        if (fld == 6) return in[3][off];
-        int i0, i1, ikx;
-        if (AXIS == 0) {
-            i0 = i;
-            i1 = col / nk;
-            ikx = col - i1 * nk;
-        } else {
-            i0 = outer;
-            i1 = i;
-            ikx = col;
-        }
-        const double Kz = __ldg(k0 + i0), Ky = __ldg(k1 + i1), Kx = __ldg(kx + ikx);
-        cplx a, b;
-        double ka, kb;
-        if (fld == 3) {  // i (Ky vz - Kz vy)
-            a = in[2][off]; b = in[1][off]; ka = Ky; kb = Kz;
-        } else if (fld == 4) {  // i (Kz vx - Kx vz)
-            a = in[0][off]; b = in[2][off]; ka = Kz; kb = Kx;
-        } else {  // i (Kx vy - Ky vx)
-            a = in[1][off]; b = in[0][off]; ka = Kx; kb = Ky;
-        }
-        const double tr = ka * a.x - kb * b.x;
-        const double ti = ka * a.y - kb * b.y;
-        cplx r = make_double2(-ti, tr);
-        if (fld == 5 && has_f && i0 == 0 && i1 == 0 && ikx == 0) r.x += f;
-        return r;
-    }
-};
-
-// ns2d: vecfft_from_rotfft + gradfft_from_fft on load.
-// /root/reference/fluidsim/solvers/ns2d/solver.py:158,165.
-struct Ns2dLoad {
+// ------------------------------------------------------------------------------- first inverse pass
+// ns2d: vecfft_from_rotfft + gradfft_from_fft applied to the prefetched value
+// (/root/reference/fluidsim/solvers/ns2d/solver.py:158,165): four outputs from one input field.
+struct Ns2dIn {
     const cplx* rot;
     const double *k1, *kx;
-    B2_DEVINL cplx operator()(int fld, long long off, int i, int col, int outer) const {
-        const cplx r = rot[off];
+    B2_DEVINL const cplx* ptr(int f, long long off, int i, int col, int outer) const { return rot + off; }
+    B2_DEVINL cplx xf(int fld, cplx r, int i, int col, int outer) const {
         const double Ky = __ldg(k1 + i), Kx = __ldg(kx + col);
         double K2 = Kx * Kx + Ky * Ky;
         if (i == 0 && col == 0) K2 = 1e-14;
         const double inv = 1.0 / K2;
         double cf;
         switch (fld) {
-            case 0: cf = Ky * inv; break;    // ux =  i KY / K2 rot
-            case 1: cf = -(Kx * inv); break; // uy = -i KX / K2 rot
-            case 2: cf = Kx; break;          // d_x rot = i KX rot
-            default: cf = Ky; break;         // d_y rot = i KY rot
+            case 0: cf = Ky * inv; break;     // ux =  i KY / K2 rot
+            case 1: cf = -(Kx * inv); break;  // uy = -i KX / K2 rot
+            case 2: cf = Kx; break;           // d_x rot = i KX rot
+            default: cf = Ky; break;          // d_y rot = i KY rot
         }
         return make_double2(-cf * r.y, cf * r.x);
     }
 };
 
+// ns3d / strat: in[] = nvar stage-input fields (v, [b]); the vorticity has already been written to
+// out[3..5] by the RK epilogue (or by b2i_curl for the first stage).  One plain launch transforms
+// v: in -> out[0..2], omega: out[3..5] in place, b: in[3] -> out[6].
 int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, cudaStream_t s) {
     if (p->solver == B2_SOLVER_NS2D) {
-        Ns2dLoad ld;
+        Ns2dIn ld;
         ld.rot = in[0];
         ld.k1 = p->k1;
         ld.kx = p->kx;
@@ -221,18 +196,13 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
     }
     const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
     const int nout = nv + 3;
+    PlainIn ld;
     PlainStore st;
     for (int f = 0; f < nout; ++f) st.out[f] = out[f];
-    if (p->n0 > 1) {
-        CurlLoad<0> ld;
-        for (int f = 0; f < nv; ++f) ld.in[f] = in[f];
-        ld.k0 = p->k0; ld.k1 = p->k1; ld.kx = p->kx; ld.nk = p->nk;
-        ld.has_f = p->has_f; ld.f = p->f;
-        return launch_strided<+1>(p->fast0, p->n0, geom_for_axis(p, 0), nout, ld, st, p->tw0, s);
-    }
-    CurlLoad<1> ld;
-    for (int f = 0; f < nv; ++f) ld.in[f] = in[f];
-    ld.k0 = p->k0; ld.k1 = p->k1; ld.kx = p->kx; ld.nk = p->nk;
-    ld.has_f = p->has_f; ld.f = p->f;
-    return launch_strided<+1>(p->fast1, p->n1, geom_for_axis(p, 1), nout, ld, st, p->tw1, s);
+    for (int f = 0; f < 3; ++f) ld.in[f] = in[f];
+    for (int f = 3; f < 6; ++f) ld.in[f] = out[f];
+    if (nv == 4) ld.in[6] = in[3];
+    const int axis = p->n0 > 1 ? 0 : 1;
+    return launch_strided<+1>(axis == 0 ? p->fast0 : p->fast1, axis == 0 ? p->n0 : p->n1,
+                              geom_for_axis(p, axis), nout, ld, st, axis == 0 ? p->tw0 : p->tw1, s);
 }

@@ -80,7 +80,7 @@ struct OpNS2D {
 template <int N>
 static int launch_c2r_n(const cplx* K, double* X, long long nlines, const cplx* tw, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
-    constexpr size_t per_ls = 2 * (size_t)PlaneSize<M>::value * sizeof(double);
+    constexpr size_t per_ls = (size_t)PlaneSize<M, 1>::value * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 48 * 1024, 256);
     auto kern = xpass_c2r_kernel<N, E, LPB>;
     const unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);
@@ -93,7 +93,7 @@ template <int N>
 static int launch_r2c_n(const double* X, cplx* K, long long nlines, const cplx* tw, double scale,
                         cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
-    constexpr size_t per_ls = 2 * (size_t)PlaneSize<M>::value * sizeof(double);
+    constexpr size_t per_ls = (size_t)PlaneSize<M, 1>::value * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 48 * 1024, 256);
     auto kern = xpass_r2c_kernel<N, E, LPB>;
     const unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);
@@ -105,7 +105,7 @@ static int launch_r2c_n(const double* X, cplx* K, long long nlines, const cplx* 
 template <int N, class Op>
 static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
-    constexpr size_t smem = (2 * (size_t)Op::NI * M + 2 * (size_t)Op::NI * PlaneSize<M>::value) * sizeof(double);
+    constexpr size_t smem = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
     auto kern = xpass_fused_fp_kernel<N, E, Op>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -121,10 +121,9 @@ static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double sca
 template <int N, class Op>
 static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
-    constexpr size_t smem_fp =
-        (2 * (size_t)Op::NI * M + 2 * (size_t)Op::NI * PlaneSize<M>::value) * sizeof(double);
+    constexpr size_t smem_fp = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
     if constexpr (T % 32 == 0 && smem_fp <= 227 * 1024) return launch_fused_fp_n<N>(op, nlines, tw, scale, s);
-    constexpr size_t per_ls = (2 * (size_t)PlaneSize<M>::value + 2 * (size_t)Op::NI * M) * sizeof(double);
+    constexpr size_t per_ls = ((size_t)PlaneSize<M, 1>::value + (size_t)Op::NI * M) * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
     static_assert(smem <= 227 * 1024, "x-pass tile does not fit shared memory");
