@@ -243,21 +243,22 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // o of the pointwise product from the parked physical lines and do its r2c.  Compared with the
 // single-group kernel this multiplies the number of resident warps per line by NI, which is what
 // the latency hiding of this pass needs (see profiles/).
-// Op additionally provides: __device__ double point1(int o, const double* u) const.
+// Op additionally provides out_of_group(g), needs(g, f) and point_g(g, u): the output formed by
+// group g (chosen so that it uses the group's own register-resident field).
 template <int N, int E, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
-    static_assert(T % 32 == 0, "field-parallel x pass needs whole warps per group");
+    static_assert(T % 32 == 0 || T == 16, "field-parallel x pass: groups are whole warps or half warps");
     const int g = threadIdx.x / T, t = threadIdx.x % T;
     const long long line = blockIdx.x;
     cplx* park = reinterpret_cast<cplx*>(b2_smem);    // [NI][E][T] complex
     cplx* plane = park + (size_t)NI * M + (size_t)g * PS;  // per-group exchange plane
     const long long loff = line * (M + 1);
     cplx x[E];
-    if constexpr (T == 32) {
+    if constexpr (T <= 32) {
         c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp());
     } else {
         c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1});
@@ -266,21 +267,25 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
     for (int m = 0; m < E; ++m) park[(g * E + m) * T + t] = x[m];
     __syncthreads();
     if (g >= NO) return;
+    // group g still holds its own physical line (field g) in registers; the other operands of
+    // output Op::out_of_group(g) come from the parked lines.
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         double ue[NI], uo[NI];
 #pragma unroll
         for (int f = 0; f < NI; ++f) {
-            const cplx v = park[(f * E + m) * T + t];
+            if (!op.needs(g, f)) continue;
+            const cplx v = (f == g) ? x[m] : park[(f * E + m) * T + t];
             ue[f] = v.x;
             uo[f] = v.y;
         }
-        x[m] = make_double2(op.point1(g, ue), op.point1(g, uo));
+        x[m] = make_double2(op.point_g(g, ue), op.point_g(g, uo));
     }
-    if constexpr (T == 32) {
-        r2c_line<N, E>(x, op.out[g] + loff, plane, t, twN, SyncWarp(), scale, true);
+    cplx* const outp = op.out[op.out_of_group(g)] + loff;
+    if constexpr (T <= 32) {
+        r2c_line<N, E>(x, outp, plane, t, twN, SyncWarp(), scale, true);
     } else {
-        r2c_line<N, E>(x, op.out[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, scale, true);
+        r2c_line<N, E>(x, outp, plane, t, twN, SyncNamed<T>{g + 1}, scale, true);
     }
 }
 

@@ -37,10 +37,17 @@ struct OpNS3D {
         r[1] = u[2] * u[3] - u[0] * u[5];
         r[2] = u[0] * u[4] - u[1] * u[3];
     }
-    B2_DEVINL double point1(int o, const double* u) const {
-        if (o == 0) return u[1] * u[5] - u[2] * u[4];
-        if (o == 1) return u[2] * u[3] - u[0] * u[5];
-        return u[0] * u[4] - u[1] * u[3];
+    // group 0 (holds vx) forms fy, group 1 (vy) forms fz, group 2 (vz) forms fx
+    B2_DEVINL int out_of_group(int g) const { return g == 0 ? 1 : (g == 1 ? 2 : 0); }
+    B2_DEVINL bool needs(int g, int f) const {
+        if (g == 0) return f == 0 || f == 2 || f == 3 || f == 5;
+        if (g == 1) return f == 0 || f == 1 || f == 3 || f == 4;
+        return f == 1 || f == 2 || f == 4 || f == 5;
+    }
+    B2_DEVINL double point_g(int g, const double* u) const {
+        if (g == 0) return u[2] * u[3] - u[0] * u[5];
+        if (g == 1) return u[0] * u[4] - u[1] * u[3];
+        return u[1] * u[5] - u[2] * u[4];
     }
 };
 // ns3d.strat: f = v x omega and v*b (div_vb_fft_from_vb, strat/solver.py:206)
@@ -56,11 +63,19 @@ struct OpStrat {
         r[4] = u[1] * u[6];
         r[5] = u[2] * u[6];
     }
-    B2_DEVINL double point1(int o, const double* u) const {
-        if (o == 0) return u[1] * u[5] - u[2] * u[4];
-        if (o == 1) return u[2] * u[3] - u[0] * u[5];
-        if (o == 2) return u[0] * u[4] - u[1] * u[3];
-        return u[o - 3] * u[6];
+    // groups 0..2 as ns3d; groups 3..5 (holding omega) form vx b, vy b, vz b
+    B2_DEVINL int out_of_group(int g) const { return g == 0 ? 1 : (g == 1 ? 2 : (g == 2 ? 0 : g)); }
+    B2_DEVINL bool needs(int g, int f) const {
+        if (g == 0) return f == 0 || f == 2 || f == 3 || f == 5;
+        if (g == 1) return f == 0 || f == 1 || f == 3 || f == 4;
+        if (g == 2) return f == 1 || f == 2 || f == 4 || f == 5;
+        return f == g - 3 || f == 6;
+    }
+    B2_DEVINL double point_g(int g, const double* u) const {
+        if (g == 0) return u[2] * u[3] - u[0] * u[5];
+        if (g == 1) return u[0] * u[4] - u[1] * u[3];
+        if (g == 2) return u[1] * u[5] - u[2] * u[4];
+        return u[g - 3] * u[6];
     }
 };
 // ns2d: Frot = -ux d_x rot - uy (d_y rot + beta)  (compute_Frot, solvers/ns2d/solver.py:34-38)
@@ -72,7 +87,9 @@ struct OpNS2D {
     B2_DEVINL void point(const double* u, double* r) const {
         r[0] = beta == 0.0 ? -u[0] * u[2] - u[1] * u[3] : -u[0] * u[2] - u[1] * (u[3] + beta);
     }
-    B2_DEVINL double point1(int o, const double* u) const {
+    B2_DEVINL int out_of_group(int g) const { return 0; }
+    B2_DEVINL bool needs(int g, int f) const { return true; }
+    B2_DEVINL double point_g(int g, const double* u) const {
         return beta == 0.0 ? -u[0] * u[2] - u[1] * u[3] : -u[0] * u[2] - u[1] * (u[3] + beta);
     }
 };
@@ -122,7 +139,8 @@ template <int N, class Op>
 static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem_fp = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
-    if constexpr (T % 32 == 0 && smem_fp <= 227 * 1024) return launch_fused_fp_n<N>(op, nlines, tw, scale, s);
+    if constexpr ((T % 32 == 0 || (T == 16 && (Op::NI * T) % 32 == 0)) && smem_fp <= 227 * 1024)
+        return launch_fused_fp_n<N>(op, nlines, tw, scale, s);
     constexpr size_t per_ls = ((size_t)PlaneSize<M, 1>::value + (size_t)Op::NI * M) * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
