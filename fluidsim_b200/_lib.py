@@ -65,6 +65,11 @@ SIGNATURES = {
     "b2_set_buffers": [_p, _p, _p, _p],
     "b2_tendencies": [_p, _p, _p, _p],
     "b2_time_step": [_p, _i, _d, _p, _p],
+    "b2_plan_create_slab": [C.POINTER(_p), _i, _i, _i, _d, _d, _d, _i, _i],
+    "b2_slab_set_buffers": [_p, _p, _p],
+    "b2_slab_phase_a": [_p, _p, _i, _p],
+    "b2_slab_phase_b": [_p, _p],
+    "b2_slab_phase_c": [_p, _i, _i, _d, _p, _p, _p, _p],
     "b2_profile_enable": [_i],
     "b2_profile_reset": [],
     "b2_profile_get": [C.POINTER(_d), C.POINTER(_ll), _i],

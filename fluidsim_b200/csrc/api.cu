@@ -57,14 +57,15 @@ static int upload_twiddles(int n, cplx** out) {
     return 0;
 }
 
-static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** out) {
+static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** out, int first = 0) {
     // fluidfft k_adim ordering: [0..n/2, -n/2+1..-1] (np.fft.fftfreq*n with +n/2 for even n)
     std::vector<double> h(nkeep > 0 ? nkeep : 1, 0.0);
     const double dk = L > 0 ? 2.0 * M_PI / L : 0.0;
-    for (int i = 0; i < nkeep; ++i) {
+    for (int j = 0; j < nkeep; ++j) {
+        const int i = first + j;
         int k = i;
         if (!half && i > n / 2) k = i - n;
-        h[i] = dk * (double)k;
+        h[j] = dk * (double)k;
     }
     CUDA_TRY(cudaMalloc((void**)out, sizeof(double) * h.size()));
     CUDA_TRY(cudaMemcpy(*out, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
@@ -112,8 +113,55 @@ extern "C" int b2_plan_create(b2_plan** out, int ndim, int n0, int n1, int n2, d
     return 0;
 }
 
+// Slab-decomposed plan (one rank of `nranks`): X space is split along z, K space along ky with the
+// local K layout (ny_loc, nz, nx/2+1), dimX_K = (1, 0, 2) -- the layout of fluidfft's
+// fft3d.mpi_with_fftwmpi3d that fluidsim already handles
+// (/root/reference/fluidsim/operators/operators3d.py:384-391).
+extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx,
+                                   int rank, int nranks) {
+    if (!out) return b2i_set_error("b2_plan_create_slab: out is NULL");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return b2i_set_error("b2_plan_create_slab: bad rank");
+    if (nz % nranks || ny % nranks)
+        return b2i_set_error("b2_plan_create_slab: nz=%d and ny=%d must be multiples of nranks=%d", nz, ny,
+                             nranks);
+    b2_plan* p = new b2_plan();
+    memset(p, 0, sizeof(*p));
+    p->ndim = 3;
+    p->slab = true;
+    p->rank = rank;
+    p->nranks = nranks;
+    p->gy = ny;
+    p->nyl = ny / nranks;
+    p->nzl = nz / nranks;
+    p->n0 = p->nyl;  // local K layout (ny_loc, nz, nk)
+    p->n1 = nz;
+    p->n2 = nx;
+    p->L0 = Ly; p->L1 = Lz; p->L2 = Lx;
+    p->nk = nx / 2 + 1;
+    p->fast0 = false;
+    p->fast1 = is_pow2(nz) && nz >= 8 && nz <= 2048;
+    p->fast2 = is_pow2(nx) && nx >= 8 && nx <= 2048;
+    p->fasty = is_pow2(ny) && ny >= 8 && ny <= 2048;
+    int e = 0;
+    e |= upload_twiddles(1, &p->tw0);
+    e |= upload_twiddles(nz, &p->tw1);
+    e |= upload_twiddles(nx, &p->tw2);
+    e |= upload_twiddles(ny, &p->twy);
+    e |= upload_wavenumbers(ny, p->nyl, Ly, false, &p->k0, rank * p->nyl);
+    e |= upload_wavenumbers(nz, nz, Lz, false, &p->k1);
+    e |= upload_wavenumbers(nx, p->nk, Lx, true, &p->kx);
+    if (e) {
+        b2_plan_destroy(p);
+        return -1;
+    }
+    p->solver = -1;
+    *out = p;
+    return 0;
+}
+
 extern "C" int b2_plan_destroy(b2_plan* p) {
     if (!p) return 0;
+    cudaFree(p->twy);
     cudaFree(p->tw0); cudaFree(p->tw1); cudaFree(p->tw2);
     cudaFree(p->k0); cudaFree(p->k1); cudaFree(p->kx);
     delete p;
@@ -127,6 +175,7 @@ extern "C" int b2_plan_shapes(const b2_plan* p, int* shapeX, int* shapeK) {
 }
 
 extern "C" int b2_plan_is_fast(const b2_plan* p) {
+    if (p->slab) return p->fast1 && p->fast2 && p->fasty;
     return (p->n0 == 1 || p->fast0) && p->fast1 && p->fast2;
 }
 
@@ -166,13 +215,22 @@ extern "C" int b2_ifft_c2r(b2_plan* p, const double* K, double* X, double* work,
 struct KGrid {
     const double *k0, *k1, *kx;
     int n0, n1, nk;
+    int swap01;            // slab K layout (ky_loc, kz, kx): axis 0 carries ky, axis 1 carries kz
+    long long origin_row;  // row holding the k = 0 mode on this rank (-1: not on this rank)
 };
-static KGrid kgrid(const b2_plan* p) { return KGrid{p->k0, p->k1, p->kx, p->n0, p->n1, p->nk}; }
+static KGrid kgrid(const b2_plan* p) {
+    return KGrid{p->k0, p->k1, p->kx, p->n0, p->n1, p->nk, p->slab ? 1 : 0,
+                 (!p->slab || p->rank == 0) ? 0LL : -1LL};
+}
 #define B2_ROW_SETUP                                         \
     const long long row = blockIdx.x;                        \
     const int i0 = (int)(row / g.n1);                        \
     const int i1 = (int)(row - (long long)i0 * g.n1);        \
-    const double Kz = g.k0[i0], Ky = g.k1[i1];               \
+    const double K0v_ = g.k0[i0], K1v_ = g.k1[i1];           \
+    const double Kz = g.swap01 ? K1v_ : K0v_;                \
+    const double Ky = g.swap01 ? K0v_ : K1v_;                \
+    const bool row_origin = row == g.origin_row;             \
+    (void)row_origin;                                        \
     const long long rbase = row * g.nk;
 static inline unsigned nrows(const b2_plan* p) { return (unsigned)((long long)p->n0 * p->n1); }
 #define B2_ROW_THREADS 128
@@ -192,7 +250,7 @@ __global__ void rot_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* 
         const long long i = rbase + ikx;
         cplx ox, oy, oz;
         curl3(Kx, Ky, Kz, vx[i], vy[i], vz[i], ox, oy, oz);
-        if (row == 0 && ikx == 0) oz.x += f;
+        if (row_origin && ikx == 0) oz.x += f;
         rx[i] = ox; ry[i] = oy; rz[i] = oz;
     }
 }
@@ -227,7 +285,7 @@ __global__ void project_kernel(KGrid g, cplx* vx, cplx* vy, cplx* vz) {
         const long long i = rbase + ikx;
         cplx a = vx[i], b = vy[i], c = vz[i];
         const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
-        project3(Kx, Ky, Kz, inv_k2_nozero(K2, row == 0 && ikx == 0), a, b, c);
+        project3(Kx, Ky, Kz, inv_k2_nozero(K2, row_origin && ikx == 0), a, b, c);
         vx[i] = a; vy[i] = b; vz[i] = c;
     }
 }
@@ -286,7 +344,7 @@ __global__ void vec_from_rot2d_kernel(KGrid g, const cplx* rot, cplx* ux, cplx* 
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         double K2 = Kx * Kx + Ky * Ky;
-        if (row == 0 && ikx == 0) K2 = 1e-14;
+        if (row_origin && ikx == 0) K2 = 1e-14;
         const double inv = 1.0 / K2;
         const cplx r = rot[i];
         const double cy = Ky * inv, cx = Kx * inv;
@@ -419,7 +477,7 @@ __global__ void exact_coefs_kernel(KGrid g, Visc v, double dt, double* exact, do
     for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
-        const double fd = freq_diss(v, K2, row == 0 && ikx == 0);
+        const double fd = freq_diss(v, K2, row_origin && ikx == 0);
         exact[rbase + ikx] = exp(-dt * fd);
         exact2[rbase + ikx] = exp(-dt / 2 * fd);
     }
@@ -673,6 +731,9 @@ extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, do
     if (solver < 0 || solver > 2) return b2i_set_error("b2_set_physics: unknown solver %d", solver);
     if ((solver == B2_SOLVER_NS2D) != (p->ndim == 2))
         return b2i_set_error("b2_set_physics: solver %d does not match a %d-D plan", solver, p->ndim);
+    if (p->slab) {
+        // wavenumber-dependent constants use the GLOBAL grid: L0/L1 were stored as (Ly, Lz)
+    }
     p->solver = solver;
     p->nu2 = nu2; p->nu4 = nu4; p->nu8 = nu8; p->num4 = num4;
     p->has_f = has_f; p->f = f; p->N = N; p->beta = beta;
@@ -726,7 +787,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
     for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
-        const bool origin = row == 0 && ikx == 0;
+        const bool origin = row_origin && ikx == 0;
         const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
         const double invK2 = inv_k2_nozero(K2, origin);
         const bool masked = a.mask ? a.mask[i] != 0 : false;
@@ -873,7 +934,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
     }
     {
         ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, W, scale, s))) return e;
+        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, s))) return e;
     }
     {
         ProfScope ps(PC_Y_FWD, s);
@@ -888,6 +949,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
 
 static int check_fused_ready(b2_plan* p, bool need_rk) {
     if (p->solver < 0) return b2i_set_error("b2_set_physics has not been called");
+    if (p->slab) return b2i_set_error("slab plans are stepped with b2_slab_phase_a/b/c (see b200spectral.h)");
     if (!b2_plan_is_fast(p))
         return b2i_set_error("fused path needs power-of-two sizes in [8, 2048] (got %d x %d x %d)", p->n0,
                              p->n1, p->n2);
@@ -966,4 +1028,101 @@ extern "C" int b2_dev_strided_pass(b2_plan* p, int axis, int dir, const double* 
         o_[f] = (cplx*)out + f * fs;
     }
     return b2i_strided_plain(p, axis, dir, i_, o_, nf, 1.0, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------- slab stepping
+// One RK stage on a slab plan = phase A, all-to-all, phase B, all-to-all, phase C; the two
+// all-to-alls (per field, equal contiguous blocks per peer) are issued by the host side through
+// torch.distributed / NCCL between the phases (fluidsim_b200/slab.py).
+extern "C" int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb) {
+    if (!p->slab) return b2i_set_error("b2_slab_set_buffers: not a slab plan");
+    p->xa = (cplx*)xa;
+    p->xb = (cplx*)xb;
+    return 0;
+}
+
+static int slab_ready(b2_plan* p) {
+    if (!p->slab) return b2i_set_error("not a slab plan");
+    if (p->solver != B2_SOLVER_NS3D && p->solver != B2_SOLVER_NS3D_STRAT)
+        return b2i_set_error("slab stepping supports ns3d and ns3d.strat");
+    if (!b2_plan_is_fast(p)) return b2i_set_error("slab stepping needs power-of-two sizes in [8, 2048]");
+    if (!p->work || !p->xa || !p->xb) return b2i_set_error("slab buffers not set");
+    return 0;
+}
+
+// phase A: (first stage: vorticity of Sin -> work[3..5]); z-inverse of v, omega, [b] into the send
+// buffers xa (exchange layout)
+extern "C" int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = slab_ready(p))) return e;
+    const long long fs = p->fsize();
+    const cplx* Sin = (const cplx*)S_in;
+    const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
+    const int nin = nv + 3;
+    if (need_curl) {
+        ProfScope ps(PC_RK, s);
+        rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, s>>>(kgrid(p), Sin, Sin + fs, Sin + 2 * fs, p->work + 3 * fs,
+                                                      p->work + 4 * fs, p->work + 5 * fs,
+                                                      p->has_f ? p->f : 0.0);
+        B2_LAUNCH_CHECK("rot_kernel");
+    }
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = 0; f < 3; ++f) in[f] = Sin + f * fs;
+    for (int f = 3; f < 6; ++f) in[f] = p->work + f * fs;
+    if (nv == 4) in[6] = Sin + 3 * fs;
+    for (int f = 0; f < nin; ++f) out[f] = p->xa + f * fs;
+    ProfScope ps(PC_FIRST_INV, s);
+    return b2i_slab_zpass(p, +1, in, out, nin, s);
+}
+
+// phase B: y-inverse, fused x pass, y-forward, in place on the receive buffers xb
+extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = slab_ready(p))) return e;
+    const long long fs = p->fsize();
+    const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
+    const int nin = nv + 3, nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
+    cplx* X[8];
+    for (int f = 0; f < nin; ++f) X[f] = p->xb + f * fs;
+    const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
+    {
+        ProfScope ps(PC_Y_INV, s);
+        if ((e = b2i_slab_ypass(p, +1, X, nin, s))) return e;
+    }
+    {
+        ProfScope ps(PC_X_FUSED, s);
+        if ((e = b2i_xpass_fused(p, X, (long long)p->gy * p->nzl, scale, s))) return e;
+    }
+    ProfScope ps(PC_Y_FWD, s);
+    return b2i_slab_ypass(p, -1, X, nout, s);
+}
+
+// phase C: z-forward from the receive buffers xa into work[0..nout-1], then the RK epilogue.
+// scheme/stage select the update (stage < 0: tendencies only, written to T_out).
+extern "C" int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S_,
+                               double* T_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = slab_ready(p))) return e;
+    const long long fs = p->fsize();
+    const int nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = 0; f < nout; ++f) { in[f] = p->xa + f * fs; out[f] = p->work + f * fs; }
+    {
+        ProfScope ps(PC_Z_FWD, s);
+        if ((e = b2i_slab_zpass(p, -1, in, out, nout, s))) return e;
+    }
+    int mode;
+    if (stage < 0) mode = M_TEND;
+    else if (scheme == B2_SCHEME_RK4 && stage < 4) mode = M_RK4_0 + stage;
+    else if (scheme == B2_SCHEME_RK2 && stage < 2) mode = M_RK2_0 + stage;
+    else return b2i_set_error("b2_slab_phase_c: bad scheme/stage %d/%d", scheme, stage);
+    if (mode != M_TEND && (!p->acc || !p->stage)) return b2i_set_error("b2_set_buffers: acc/stage missing");
+    RKArgs a = rk_args(p, (const cplx*)S_in, (cplx*)S_, dt);
+    a.Tout = (cplx*)T_out;
+    return launch_rk_stage(p, mode, a, s);
 }

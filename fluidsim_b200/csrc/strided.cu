@@ -206,3 +206,70 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
     return launch_strided<+1>(axis == 0 ? p->fast0 : p->fast1, axis == 0 ? p->n0 : p->n1,
                               geom_for_axis(p, axis), nout, ld, st, axis == 0 ? p->tw0 : p->tw1, s);
 }
+
+// ------------------------------------------------------------------------------- slab passes
+// Index map between K-layout coordinates (yl = outer, z = i, kx = col) and the exchange layout
+// [peer r = z / nzl][yl][zl = z % nzl][kx] of one field.
+struct SlabMapper {
+    int nzl, nyl, nk;
+    B2_DEVINL long long operator()(int z, int kx, int yl) const {
+        const int r = z / nzl;
+        const int zl = z - r * nzl;
+        return (((long long)r * nyl + yl) * nzl + zl) * nk + kx;
+    }
+};
+struct SlabStore {
+    cplx* out[B2_MAXF];
+    SlabMapper map;
+    B2_DEVINL void operator()(int f, long long off, int i, int col, int outer, cplx v) const {
+        out[f][map(i, col, outer)] = v;
+    }
+};
+struct SlabIn {
+    const cplx* in[B2_MAXF];
+    SlabMapper map;
+    B2_DEVINL const cplx* ptr(int f, long long off, int i, int col, int outer) const {
+        return in[f] + map(i, col, outer);
+    }
+    B2_DEVINL cplx xf(int f, cplx v, int i, int col, int outer) const { return v; }
+};
+
+int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s) {
+    if (nf > B2_MAXF) return b2i_set_error("too many fields");
+    Geom g;
+    g.ncols = p->nk;
+    g.nouter = p->n0;  // ny_loc
+    g.es = p->nk;
+    g.os = (long long)p->n1 * p->nk;
+    g.cs = 1;
+    g.nf = nf;
+    const SlabMapper map{p->nzl, p->nyl, p->nk};
+    if (dir > 0) {
+        PlainIn ld;
+        SlabStore st;
+        st.map = map;
+        for (int f = 0; f < nf; ++f) { ld.in[f] = in[f]; st.out[f] = out[f]; }
+        return launch_strided<+1>(p->fast1, p->n1, g, nf, ld, st, p->tw1, s);
+    }
+    SlabIn ld;
+    ld.map = map;
+    PlainStore st;
+    for (int f = 0; f < nf; ++f) { ld.in[f] = in[f]; st.out[f] = out[f]; }
+    return launch_strided<-1>(p->fast1, p->n1, g, nf, ld, st, p->tw1, s);
+}
+
+int b2i_slab_ypass(b2_plan* p, int dir, cplx* const* bufs, int nf, cudaStream_t s) {
+    if (nf > B2_MAXF) return b2i_set_error("too many fields");
+    Geom g;
+    g.ncols = p->nzl * p->nk;
+    g.nouter = 1;
+    g.es = (long long)p->nzl * p->nk;
+    g.os = 0;
+    g.cs = 1;
+    g.nf = nf;
+    PlainIn ld;
+    PlainStore st;
+    for (int f = 0; f < nf; ++f) { ld.in[f] = bufs[f]; st.out[f] = bufs[f]; }
+    return dir < 0 ? launch_strided<-1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s)
+                   : launch_strided<+1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s);
+}

@@ -257,8 +257,7 @@ int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream
 }
 
 template <class Op>
-static int launch_fused(b2_plan* p, Op op, double scale, cudaStream_t s) {
-    const long long nlines = (long long)p->n0 * p->n1;
+static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, cudaStream_t s) {
     switch (p->n2) {
 #define B2_CASE(n) case n: return launch_fused_n<n>(op, nlines, p->tw2, scale, s);
         B2_XSIZES(B2_CASE)
@@ -267,23 +266,23 @@ static int launch_fused(b2_plan* p, Op op, double scale, cudaStream_t s) {
     return b2i_set_error("fused x pass: nx=%d not supported (power of two in [8, 2048])", p->n2);
 }
 
-int b2i_xpass_fused(b2_plan* p, cplx* const* W, double scale, cudaStream_t s) {
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, cudaStream_t s) {
     if (!p->fast2) return b2i_set_error("fused x pass needs a power-of-two nx");
     if (p->solver == B2_SOLVER_NS3D) {
         OpNS3D op;
         for (int f = 0; f < 6; ++f) op.in[f] = W[f];
         for (int f = 0; f < 3; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, scale, s);
+        return launch_fused(p, op, nlines, scale, s);
     }
     if (p->solver == B2_SOLVER_NS3D_STRAT) {
         OpStrat op;
         for (int f = 0; f < 7; ++f) op.in[f] = W[f];
         for (int f = 0; f < 6; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, scale, s);
+        return launch_fused(p, op, nlines, scale, s);
     }
     OpNS2D op;
     for (int f = 0; f < 4; ++f) op.in[f] = W[f];
     op.out[0] = W[0];
     op.beta = p->beta;
-    return launch_fused(p, op, scale, s);
+    return launch_fused(p, op, nlines, scale, s);
 }

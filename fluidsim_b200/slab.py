@@ -1,0 +1,186 @@
+"""Slab-decomposed (multi-GPU) time stepping: one process per GPU, ``torch.distributed`` for the
+plumbing, the two global transposes of every 3-D FFT as NCCL all-to-alls between the CUDA phases.
+
+Decomposition (the layout fluidsim already handles for
+``fft3d.mpi_with_fftwmpi3d``, ``/root/reference/fluidsim/operators/operators3d.py:384-391``):
+
+* physical / semi-spectral side: split along z -> local ``(ny, nz_loc, .)`` line sets
+* spectral side: split along ky -> local K layout ``(ny_loc, nz, nx/2+1)``, ``dimX_K = (1, 0, 2)``
+
+One RK stage = phase A (z-inverse written straight into the exchange layout: the "pack" is fused
+into the FFT store), all-to-all, phase B (y-inverse, fused x pass, y-forward, in place on the
+received blocks: no "unpack" pass either), all-to-all, phase C (z-forward reading the exchange
+layout + RK epilogue).  The exchange layout of a field is ``[peer][ky_loc][z_loc][kx]``, so each
+all-to-all moves ``world`` equal contiguous blocks per field and the received buffer *is* the
+``(ny, nz_loc, nk)`` array the y pass wants.
+
+The functions ``local_from_global`` / ``global_from_local`` / ``exchange_index`` define the layout
+algebra and are exercised on CPU (gloo, world_size 2) in ``tests/test_slab_cpu.py``.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import SCHEME_IDS, SOLVER_IDS
+
+
+# ----------------------------------------------------------------------------------- layout algebra
+def local_from_global(arr_global, rank, world):
+    """Global sequential K array ``(..., nz, ny, nk)`` -> this rank's ``(..., ny_loc, nz, nk)``."""
+    ny = arr_global.shape[-2]
+    nyl = ny // world
+    sl = arr_global[..., :, rank * nyl:(rank + 1) * nyl, :]
+    return np.ascontiguousarray(np.swapaxes(sl, -3, -2))
+
+
+def global_from_local(parts):
+    """Inverse of ``local_from_global`` given the list of all ranks' local arrays."""
+    return np.ascontiguousarray(np.concatenate([np.swapaxes(p, -3, -2) for p in parts], axis=-2))
+
+
+def exchange_index(z, kx, yl, nzl, nyl, nk):
+    """Offset of K-layout element (yl, z, kx) in the exchange layout [peer][ky_loc][z_loc][kx]
+    (restated by ``SlabMapper`` in csrc/strided.cu)."""
+    r = z // nzl
+    zl = z - r * nzl
+    return ((r * nyl + yl) * nzl + zl) * nk + kx
+
+
+def check_divisible(nz, ny, world):
+    if nz % world or ny % world:
+        raise ValueError(f"slab decomposition needs nz={nz} and ny={ny} to be multiples of world={world}")
+
+
+# ----------------------------------------------------------------------------------- GPU solver
+class SlabSimul:
+    """Distributed ns3d / ns3d.strat RK2 / RK4 stepping on a slab plan.
+
+    ``params`` uses the reference's attribute names (see ``fluidsim_b200.params``).  The local
+    state is ``state_spect`` of shape ``(nvar, ny_loc, nz, nk)``.
+    """
+
+    def __init__(self, solver, params, group=None):
+        import torch
+        import torch.distributed as dist
+
+        from ._lib import call, ptr
+
+        if solver not in ("ns3d", "ns3d.strat"):
+            raise NotImplementedError("slab decomposition is implemented for ns3d and ns3d.strat")
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (one process per GPU)")
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.solver = solver
+        self.params = params
+        po = params.oper
+        self.nx, self.ny, self.nz = int(po.nx), int(po.ny), int(po.nz)
+        check_divisible(self.nz, self.ny, self.world)
+        self.nyl, self.nzl = self.ny // self.world, self.nz // self.world
+        self.nk = self.nx // 2 + 1
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        handle = C.c_void_p()
+        call("b2_plan_create_slab", C.byref(handle), self.nz, self.ny, self.nx, float(po.Lz), float(po.Ly),
+             float(po.Lx), self.rank, self.world)
+        self.handle = handle
+        self.shapeK_loc = (self.nyl, self.nz, self.nk)
+        self.nvar = 4 if solver == "ns3d.strat" else 3
+        self.nwork = self.nvar + 3
+        self.nout = 3 if solver == "ns3d" else 6
+        mk = lambda n: torch.zeros((n,) + self.shapeK_loc, dtype=torch.complex128, device=self.device)
+        self.state_spect = mk(self.nvar)
+        self._acc, self._stagebuf = mk(self.nvar), mk(self.nvar)
+        self._work, self._xa, self._xb = mk(self.nwork), mk(self.nwork), mk(self.nwork)
+        self.where_dealiased = None  # local uint8 mask (ny_loc, nz, nk); set_mask_from_global
+        self.deltat = float(params.time_stepping.deltat0)
+        self.scheme = params.time_stepping.type_time_scheme
+        if self.scheme not in SCHEME_IDS:
+            raise ValueError(f'Problem name time_scheme ("{self.scheme}")')
+        self.it = 0
+        self.t = 0.0
+        self._scalar = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._push()
+
+    def _push(self):
+        from ._lib import call, ptr
+
+        p = self.params
+        f = getattr(p, "f", None)
+        call("b2_set_physics", self.handle, SOLVER_IDS[self.solver], float(p.nu_2), float(p.nu_4),
+             float(p.nu_8), float(p.nu_m4), 0 if f is None else 1, 0.0 if f is None else float(f),
+             float(getattr(p, "N", 0.0)), 0.0, ptr(self.where_dealiased))
+        call("b2_set_buffers", self.handle, ptr(self._acc), ptr(self._stagebuf), ptr(self._work))
+        call("b2_slab_set_buffers", self.handle, ptr(self._xa), ptr(self._xb))
+
+    # ---- data in / out ---------------------------------------------------------------------------
+    def set_mask_from_global(self, mask_global):
+        """``where_dealiased`` of the sequential operator ``(nz, ny, nk)`` -> local slab."""
+        loc = local_from_global(np.asarray(mask_global, dtype=np.uint8), self.rank, self.world)
+        self.where_dealiased = self.torch.from_numpy(loc).to(self.device)
+        self._push()
+
+    def set_state_from_global(self, state_global):
+        loc = local_from_global(np.asarray(state_global), self.rank, self.world)
+        self.state_spect.copy_(self.torch.from_numpy(loc))
+
+    def gather_state(self):
+        """Global sequential-layout state on every rank (testing / small grids only)."""
+        parts = [self.torch.empty_like(self.state_spect) for _ in range(self.world)]
+        self.dist.all_gather(parts, self.state_spect, group=self.group)
+        return global_from_local([p.cpu().numpy() for p in parts])
+
+    # ---- collectives ------------------------------------------------------------------------------
+    def _all_to_all(self, src, dst, nf):
+        """Per field: ``world`` equal contiguous blocks (NCCL over NVLink; gloo on CPU tests)."""
+        tr = self.torch
+        for f in range(nf):
+            self.dist.all_to_all_single(tr.view_as_real(dst[f]).view(-1), tr.view_as_real(src[f]).view(-1),
+                                        group=self.group)
+
+    # ---- stepping ---------------------------------------------------------------------------------
+    def _run_stage(self, Sin, need_curl, scheme_id, stage, tout=None):
+        from ._lib import call, ptr, stream_ptr
+
+        h = self.handle
+        call("b2_slab_phase_a", h, ptr(Sin), 1 if need_curl else 0, stream_ptr())
+        self._all_to_all(self._xa, self._xb, self.nwork)
+        call("b2_slab_phase_b", h, stream_ptr())
+        self._all_to_all(self._xb, self._xa, self.nout)
+        call("b2_slab_phase_c", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout),
+             stream_ptr())
+
+    def tendencies_nonlin(self, state_spect=None, old=None):
+        src = self.state_spect if state_spect is None else state_spect
+        out = self.torch.empty_like(self.state_spect) if old is None else old
+        self._run_stage(src, True, SCHEME_IDS[self.scheme], -1, out)
+        return out
+
+    def one_time_step(self):
+        sid = SCHEME_IDS[self.scheme]
+        nstages = 4 if self.scheme == "RK4" else 2
+        for st in range(nstages):
+            Sin = self.state_spect if st == 0 else self._stagebuf
+            self._run_stage(Sin, st == 0, sid, st)
+        self.t += self.deltat
+        self.it += 1
+
+    def compute_energy(self):
+        """sum_wavenumbers(|v|^2)/2 over the velocity components, all-reduced."""
+        from ._lib import call, ptr, stream_ptr
+
+        call("b2_sum_wavenumbers_abs2", self.handle, ptr(self.state_spect), 3, ptr(self._scalar), stream_ptr())
+        self.dist.all_reduce(self._scalar, group=self.group)
+        return 0.5 * float(self._scalar.item())
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+
+            if getattr(self, "handle", None):
+                lib.b2_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -131,6 +131,23 @@ int b2_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream);
 /* one full step of `scheme` with time increment dt, in place on S, including the final
  * project_state_spect + dealiasing of one_time_step_computation. */
 int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
+/* ---- slab decomposition over the GPUs of one node.  One plan per rank; X
+ * space split along z, K space along ky: local K layout (ny/P, nz, nx/2+1), dimX_K = (1,0,2), the
+ * layout of fluidfft's fft3d.mpi_with_fftwmpi3d (operators/operators3d.py:384-391).  The fused
+ * stage is cut at its two global transposes: phase A (z-inverse into send buffers), all-to-all,
+ * phase B (y-inverse, fused x pass, y-forward), all-to-all, phase C (z-forward + RK epilogue).
+ * The all-to-alls exchange, per field, nranks equal contiguous blocks (xa -> xb after phase A for
+ * nvar+3 fields, xb -> xa after phase B for 3 (ns3d) / 6 (strat) fields) and are issued by the host
+ * side (torch.distributed / NCCL; fluidsim_b200/slab.py). */
+int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx, int rank,
+                        int nranks);
+int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb);
+int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream);
+int b2_slab_phase_b(b2_plan* p, void* stream);
+/* stage < 0: tendencies only (written to T_out); else stage of `scheme`, updating acc/stage/S */
+int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S,
+                    double* T_out, void* stream);
+
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 long long b2_launch_count(void);
 

@@ -1,0 +1,87 @@
+"""Multi-GPU (slab) parity: N ranks over NCCL must reproduce the reference golden vectors.
+Needs >= 2 GPUs (run with `gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, name, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from fluidsim_b200.params import create_default_params
+        from fluidsim_b200.slab import SlabSimul
+
+        meta, z = load_golden(name)
+        solver = meta["solver"]
+        kw = dict(meta["params"])
+        p = create_default_params(solver)
+        p.oper.nx, p.oper.ny, p.oper.nz = meta["shape"]
+        for key in ("Lx", "Ly", "Lz"):
+            if key in kw:
+                setattr(p.oper, key, kw.pop(key))
+        p.time_stepping.type_time_scheme = kw.pop("type_time_scheme", "RK4")
+        p.time_stepping.deltat0 = kw.pop("deltat0")
+        for key in list(kw):
+            setattr(p, key, kw.pop(key))
+        sim = SlabSimul(solver, p)
+        sim.set_mask_from_global(z["mask"])
+        sim.set_state_from_global(z["state0"])
+        tend = sim.tendencies_nonlin()
+        parts = [torch.empty_like(tend) for _ in range(world)]
+        dist.all_gather(parts, tend)
+        from fluidsim_b200.slab import global_from_local
+
+        e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts]), z["tend0"])
+        sim.one_time_step()
+        e_1 = rel_err(sim.gather_state(), z["state1"])
+        for _ in range(meta["nsteps"] - 1):
+            sim.one_time_step()
+        e_n = rel_err(sim.gather_state(), z["stateN"])
+        e_en = abs(sim.compute_energy() - float(z["energyN"])) / float(z["energyN"])
+        q.put((rank, e_t, e_1, e_n, e_en))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "strat_16x8x32_rk2"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_matches_reference_golden(name, world):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    meta, _ = load_golden(name)
+    nx, ny, nz = meta["shape"]
+    if nz % world or ny % world:
+        pytest.skip("grid not divisible")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() + world * 7 + len(name)) % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(300)
+        assert pr.exitcode == 0
+    for _ in range(world):
+        rank, e_t, e_1, e_n, e_en = q.get(timeout=10)
+        assert e_t < 1e-11, (rank, e_t)
+        assert e_1 < 1e-11, (rank, e_1)
+        assert e_n < 1e-10, (rank, e_n)
+        assert e_en < 1e-8
