@@ -2,7 +2,7 @@
 """Benchmark of the pseudo-spectral RK4 step (BASELINE.json metric: ns3d RK4 steps/s and
 grid-pts*steps/s), own arm (CUDA, libb200spectral) and reference arm (CPU, oracle port).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n 512] [--solver ns3d]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--size 512] [--solver ns3d]
 
 Prints ONE JSON line (rank 0).  A "step" is one full RK4 time step (4 evaluations of the nonlinear
 term = 36 3-D FFTs + epilogues) of the named solver on a synthetic noise field; protocol restated
@@ -43,13 +43,24 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="grid size per axis (power of two)")
+    ap.add_argument("--size", dest="n", type=int, default=1024, help="grid size per axis (power of two)")
     ap.add_argument("--solver", default="ns3d", choices=["ns3d", "ns3d.strat", "ns2d"])
     ap.add_argument("--scheme", default="RK4", choices=["RK4", "RK2"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-n", type=int, default=128, help="grid size of the bounded CPU sample")
     return ap.parse_args()
+
+
+def host_mem_available():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
 
 
 def peaks():
@@ -157,7 +168,7 @@ def reference_arm(args):
         "warmup": min(args.warmup, 1),
         "ms_per_step": r["ms_per_step"],
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": "strong",
         "vs_baseline": None,
         "dtype": "f64",
         "data": "synthetic",
@@ -228,6 +239,52 @@ def init_noise_on_device(sim, torch, seed=42):
     sim.state.mark_spect_modified()
 
 
+def make_slab_sim(args, torch, dist):
+    """N > 1: slab decomposition (fluidsim_b200.slab.SlabSimul), same protocol, strong scaling."""
+    import math
+
+    from fluidsim_b200._lib import call, ptr, stream_ptr
+    from fluidsim_b200.params import create_default_params
+    from fluidsim_b200.slab import SlabSimul
+
+    p = create_default_params(args.solver)
+    n = args.n
+    p.oper.nx = p.oper.ny = p.oper.nz = n
+    p.nu_8 = 1.0
+    p.time_stepping.USE_CFL = False
+    p.time_stepping.deltat0 = 1e-4
+    p.time_stepping.type_time_scheme = args.scheme
+    sim = SlabSimul(args.solver, p)
+    dev = sim.device
+    dk = 2 * math.pi / (2 * math.pi)
+    kadim = lambda m: torch.fft.fftfreq(m, 1.0 / m, dtype=torch.float64, device=dev).abs()
+    ky = dk * kadim(n)[sim.rank * sim.nyl:(sim.rank + 1) * sim.nyl]
+    kz = dk * kadim(n)
+    kx = dk * torch.arange(n // 2 + 1, dtype=torch.float64, device=dev)
+    c = 2.0 / 3
+    lim = c * dk * (n // 2 + 1)
+    mask = ((ky >= lim)[:, None, None] | (kz >= lim)[None, :, None] | (kx >= lim)[None, None, :])
+    sim.where_dealiased = mask.to(torch.uint8).contiguous()
+    sim._push()
+    g = torch.Generator(device=dev).manual_seed(42 + sim.rank)
+    S = sim.state_spect
+    k0 = 2 * math.pi / (2 * math.pi / 4.0)
+    for i in range(sim.nvar):
+        tmp = torch.view_as_real(S[i])
+        tmp.uniform_(-0.5, 0.5, generator=g)
+    for a in range(0, sim.nyl, max(1, sim.nyl // 8)):
+        b = min(sim.nyl, a + max(1, sim.nyl // 8))
+        K = torch.sqrt(ky[a:b, None, None] ** 2 + kz[None, :, None] ** 2 + kx[None, None, :] ** 2)
+        S[:, a:b] *= (1.0 + torch.tanh(2 * math.pi * (k0 - K) / k0)) / 2.0
+    if sim.rank == 0:
+        S[:, 0, 0, 0] = 0.0
+    call("b2_project_perpk3d", sim.handle, ptr(S[0]), ptr(S[1]), ptr(S[2]), stream_ptr())
+    call("b2_dealias", sim.handle, ptr(S), sim.nvar, ptr(sim.where_dealiased), stream_ptr())
+    e = sim.compute_energy()
+    S *= (0.045 / e) ** 0.5
+    return sim
+
+
 def own_arm(args):
     import torch
     import torch.distributed as dist
@@ -239,15 +296,25 @@ def own_arm(args):
         raise RuntimeError("bench.py (own arm) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     from fluidsim_b200 import _lib
 
     hbm_peak, peak_src = peaks()
-    sim = make_sim(args, torch)
-    ts = sim.time_stepping
-    S = sim.state.state_spect.tensor
-    npts = float(args.n) ** sim.ndim
-    F = 16.0 * S[0].numel()
+    if world > 1:
+        sim = make_slab_sim(args, torch, dist)
+        ts = sim
+        S = sim.state_spect
+        ndim = 3
+    else:
+        sim = make_sim(args, torch)
+        ts = sim.time_stepping
+        S = sim.state.state_spect.tensor
+        ndim = sim.ndim
+    npts = float(args.n) ** ndim
+    F = 16.0 * S[0].numel()  # local field pass (per GPU)
 
     def barrier():
         if world > 1:
@@ -274,21 +341,25 @@ def own_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * npts / (ms_per_step * 1e-3)
+    value = npts / (ms_per_step * 1e-3)  # whole job: the N ranks advance ONE n^3 grid (strong scaling)
     if not bool(torch.isfinite(S.real.sum()).item()):
         raise RuntimeError("state became non finite during the benchmark")
 
     # ---- per-kernel-class timing (CUDA events on the launching stream inside the library)
     roofline = None
     classes = {}
-    if rank == 0:
-        import ctypes as C
+    import ctypes as C
 
-        _lib.lib.b2_profile_reset()
-        _lib.lib.b2_profile_enable(1)
-        nprof = max(2, min(args.steps, 5))
-        for _ in range(nprof):
-            ts.one_time_step()
+    # every rank runs the profiled steps (they contain collectives); rank 0 reports its own timings
+    _lib.lib.b2_profile_reset()
+    _lib.lib.b2_profile_enable(1)
+    nprof = max(2, min(args.steps, 5))
+    for _ in range(nprof):
+        ts.one_time_step()
+    torch.cuda.synchronize()
+    if rank != 0:
+        _lib.lib.b2_profile_enable(0)
+    if rank == 0:
         msarr = (C.c_double * 6)()
         cnt = (C.c_longlong * 6)()
         _lib.lib.b2_profile_get(msarr, cnt, 6)
@@ -314,7 +385,10 @@ def own_arm(args):
 
     # ---- end to end through the public API with HOST buffers (state in pinned host memory)
     e2e = None
-    if not args.no_e2e and world == 1:
+    e2e_note = None
+    if not args.no_e2e and world == 1 and host_mem_available() < 3 * S.numel() * 16:
+        e2e_note = "skipped: not enough host memory for a pinned copy of the state"
+    elif not args.no_e2e and world == 1:
         host = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
         host.copy_(S)
         torch.cuda.synchronize()
@@ -336,12 +410,19 @@ def own_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_run(args.solver, args.scheme, args.cpu_n, 10, 1, max_seconds=20.0)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                        "sample": f"{args.solver} {r['n']}^{sim.ndim} {args.scheme}, {r['steps']} steps of the numpy/"
+                        "sample": f"{args.solver} {r['n']}^{ndim} {args.scheme}, {r['steps']} steps of the numpy/"
                                   f"pocketfft oracle port, {r['ms_per_step']:.0f} ms/step"}
 
     if rank == 0:
         step_passes = STEP_PASSES.get((args.solver, args.scheme))
-        step_alg = step_passes * F / world if step_passes else None
+        step_alg = step_passes * F if step_passes else None  # per GPU (F is the local field pass)
+        nfft = {"ns3d": 36, "ns3d.strat": 52}.get(args.solver, 0) if args.scheme == "RK4" else 0
+        nvlink = None
+        if world > 1:
+            nvl_bytes = nfft * F * (world - 1) / world  # sent per GPU per direction per step
+            nvlink = {"bytes_per_gpu_per_step": nvl_bytes, "peak_GBps": 770.0,
+                      "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
+                      "floor_ms": nvl_bytes / 770e9 * 1e3}
         line = {
             "metric": METRIC if args.solver == "ns3d" else f"{args.solver}_{args.scheme.lower()}_grid_points_steps_per_s",
             "value": value,
@@ -352,18 +433,19 @@ def own_arm(args):
             "ms_per_step": ms_per_step,
             "steps_per_s": 1e3 / ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f64",
             "data": "synthetic",
             "config": {
-                "workload": f"{args.solver} {args.n}^{sim.ndim} {args.scheme} float64, noise init, nu_8=1, dt=1e-4, "
+                "workload": f"{args.solver} {args.n}^{ndim} {args.scheme} float64, noise init, nu_8=1, dt=1e-4, "
                             "USE_CFL=False (fluidsim-bench protocol; forcing off)",
                 "n": args.n,
-                "state_bytes": S.numel() * 16,
+                "state_bytes_per_gpu": S.numel() * 16,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
-                "parallelism": "single GPU" if world == 1 else f"replicas x{world}",
+                "parallelism": "single GPU" if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all)",
             },
+            "nvlink": nvlink,
             "roofline": roofline,
             "step_roofline": {
                 "model_field_passes": step_passes,
@@ -373,7 +455,7 @@ def own_arm(args):
             },
             "kernel_classes": classes,
             "cpu_baseline": cpu_baseline,
-            "e2e": e2e,
+            "e2e": e2e if e2e is not None else ({"note": e2e_note} if e2e_note else None),
             "gpu_launches": launches,
             "clocks": clocks,
         }
