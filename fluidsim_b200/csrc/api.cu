@@ -215,23 +215,48 @@ extern "C" int b2_ifft_c2r(b2_plan* p, const double* K, double* X, double* work,
 struct KGrid {
     const double *k0, *k1, *kx;
     int n0, n1, nk;
-    int swap01;            // slab K layout (ky_loc, kz, kx): axis 0 carries ky, axis 1 carries kz
-    long long origin_row;  // row holding the k = 0 mode on this rank (-1: not on this rank)
+    int swap01;      // slab K layout (ky_loc, kz, kx): axis 0 carries ky, axis 1 carries kz
+    int has_origin;  // the k = 0 mode lives on this rank (row 0)
+    // visited rows / columns (dealias-pruned fused path; identity otherwise): compact row index
+    // (j0, j1) -> (i0, i1) by j < lo ? j : j + gap ; kx < nkx
+    int n1c, r0_lo, r0_gap, r1_lo, r1_gap, nkx;
 };
 static KGrid kgrid(const b2_plan* p) {
-    return KGrid{p->k0, p->k1, p->kx, p->n0, p->n1, p->nk, p->slab ? 1 : 0,
-                 (!p->slab || p->rank == 0) ? 0LL : -1LL};
+    KGrid g;
+    g.k0 = p->k0; g.k1 = p->k1; g.kx = p->kx;
+    g.n0 = p->n0; g.n1 = p->n1; g.nk = p->nk;
+    g.swap01 = p->slab ? 1 : 0;
+    g.has_origin = (!p->slab || p->rank == 0) ? 1 : 0;
+    g.n1c = p->n1; g.r0_lo = 1 << 30; g.r0_gap = 0; g.r1_lo = 1 << 30; g.r1_gap = 0; g.nkx = p->nk;
+    return g;
 }
-#define B2_ROW_SETUP                                         \
-    const long long row = blockIdx.x;                        \
-    const int i0 = (int)(row / g.n1);                        \
-    const int i1 = (int)(row - (long long)i0 * g.n1);        \
-    const double K0v_ = g.k0[i0], K1v_ = g.k1[i1];           \
-    const double Kz = g.swap01 ? K1v_ : K0v_;                \
-    const double Ky = g.swap01 ? K0v_ : K1v_;                \
-    const bool row_origin = row == g.origin_row;             \
-    (void)row_origin;                                        \
-    const long long rbase = row * g.nk;
+// grid of the fused path: only the bounding box of the non-dealiased modes when pruning is on
+static KGrid kgrid_fused(const b2_plan* p) {
+    KGrid g = kgrid(p);
+    if (p->prune) {
+        g.r0_lo = p->keep0_lo; g.r0_gap = p->keep0_hi - p->keep0_lo;
+        g.r1_lo = p->keep1_lo; g.r1_gap = p->keep1_hi - p->keep1_lo;
+        g.n1c = p->keep1_lo + (p->n1 - p->keep1_hi);
+        g.nkx = p->keepx;
+    }
+    return g;
+}
+static inline unsigned nrows_fused(const b2_plan* p) {
+    if (!p->prune) return (unsigned)((long long)p->n0 * p->n1);
+    return (unsigned)((long long)(p->keep0_lo + (p->n0 - p->keep0_hi)) * (p->keep1_lo + (p->n1 - p->keep1_hi)));
+}
+#define B2_ROW_SETUP                                                     \
+    const long long row = blockIdx.x;                                    \
+    const int j0_ = (int)(row / g.n1c);                                  \
+    const int j1_ = (int)(row - (long long)j0_ * g.n1c);                 \
+    const int i0 = j0_ < g.r0_lo ? j0_ : j0_ + g.r0_gap;                 \
+    const int i1 = j1_ < g.r1_lo ? j1_ : j1_ + g.r1_gap;                 \
+    const double K0v_ = g.k0[i0], K1v_ = g.k1[i1];                       \
+    const double Kz = g.swap01 ? K1v_ : K0v_;                            \
+    const double Ky = g.swap01 ? K0v_ : K1v_;                            \
+    const bool row_origin = g.has_origin && i0 == 0 && i1 == 0;          \
+    (void)row_origin;                                                    \
+    const long long rbase = ((long long)i0 * g.n1 + i1) * g.nk;
 static inline unsigned nrows(const b2_plan* p) { return (unsigned)((long long)p->n0 * p->n1); }
 #define B2_ROW_THREADS 128
 
@@ -245,7 +270,7 @@ B2_DEVINL void curl3(double Kx, double Ky, double Kz, cplx a, cplx b, cplx c, cp
 __global__ void rot_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* vz, cplx* rx, cplx* ry,
                            cplx* rz, double f) {
     B2_ROW_SETUP
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         cplx ox, oy, oz;
@@ -257,7 +282,7 @@ __global__ void rot_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* 
 
 __global__ void div_kernel(KGrid g, const cplx* vx, const cplx* vy, const cplx* vz, cplx* d) {
     B2_ROW_SETUP
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         const cplx a = vx[i], b = vy[i], c = vz[i];
@@ -280,7 +305,7 @@ B2_DEVINL void project3(double Kx, double Ky, double Kz, double invK2, cplx& a, 
 
 __global__ void project_kernel(KGrid g, cplx* vx, cplx* vy, cplx* vz) {
     B2_ROW_SETUP
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         cplx a = vx[i], b = vy[i], c = vz[i];
@@ -340,7 +365,7 @@ __global__ void add_kernel(cplx* a, const cplx* b, long long n) {
 __global__ void vec_from_rot2d_kernel(KGrid g, const cplx* rot, cplx* ux, cplx* uy) {
     B2_ROW_SETUP
     (void)Kz;
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         double K2 = Kx * Kx + Ky * Ky;
@@ -355,7 +380,7 @@ __global__ void vec_from_rot2d_kernel(KGrid g, const cplx* rot, cplx* ux, cplx* 
 __global__ void grad2d_kernel(KGrid g, const cplx* f, cplx* px, cplx* py) {
     B2_ROW_SETUP
     (void)Kz;
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         const cplx r = f[i];
@@ -366,7 +391,7 @@ __global__ void grad2d_kernel(KGrid g, const cplx* f, cplx* px, cplx* py) {
 __global__ void rot2d_kernel(KGrid g, const cplx* ux, const cplx* uy, cplx* rot) {
     B2_ROW_SETUP
     (void)Kz;
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         const cplx a = ux[i], b = uy[i];
@@ -474,7 +499,7 @@ B2_DEVINL double freq_diss(const Visc& v, double K2, bool is_origin) {
 
 __global__ void exact_coefs_kernel(KGrid g, Visc v, double dt, double* exact, double* exact2) {
     B2_ROW_SETUP
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
         const double fd = freq_diss(v, K2, row_origin && ikx == 0);
@@ -726,6 +751,78 @@ extern "C" int b2_profile_get(double* ms, long long* count, int ncat) {
 }
 
 // ------------------------------------------------------------------------------- fused path
+// per-axis "some mode is kept" flags of the dealiasing mask (bounding box of the kept modes)
+__global__ void mask_bounds_kernel(const uint8_t* mask, int n0, int n1, int nk, int* keep0, int* keep1,
+                                   int* keepx) {
+    const long long row = blockIdx.x;
+    const int i0 = (int)(row / n1), i1 = (int)(row % n1);
+    bool any = false;
+    for (int ikx = threadIdx.x; ikx < nk; ikx += blockDim.x) {
+        if (!mask[row * nk + ikx]) {
+            any = true;
+            keepx[ikx] = 1;
+        }
+    }
+    if (any) {
+        keep0[i0] = 1;
+        keep1[i1] = 1;
+    }
+}
+
+static void kept_range(const std::vector<int>& keep, int n, int* lo, int* hi) {
+    // kept indices are contained in [0, lo) U [hi, n)
+    int l = 0, h = n;
+    for (int i = 0; i <= n / 2 && i < n; ++i)
+        if (keep[i]) l = i + 1;
+    for (int i = n - 1; i > n / 2; --i)
+        if (keep[i]) h = i;
+    if (h < l) h = l;
+    *lo = l;
+    *hi = h;
+}
+
+static int compute_mask_bounds(b2_plan* p) {
+    p->keep0_lo = p->n0; p->keep0_hi = p->n0;
+    p->keep1_lo = p->n1; p->keep1_hi = p->n1;
+    p->keepx = p->nk;
+    if (!p->mask) return 0;
+    int* d = nullptr;
+    const int tot = p->n0 + p->n1 + p->nk;
+    CUDA_TRY(cudaMalloc((void**)&d, sizeof(int) * tot));
+    CUDA_TRY(cudaMemset(d, 0, sizeof(int) * tot));
+    mask_bounds_kernel<<<(unsigned)((long long)p->n0 * p->n1), 128>>>(p->mask, p->n0, p->n1, p->nk, d, d + p->n0,
+                                                                     d + p->n0 + p->n1);
+    B2_LAUNCH_CHECK("mask_bounds_kernel");
+    std::vector<int> h(tot);
+    CUDA_TRY(cudaMemcpy(h.data(), d, sizeof(int) * tot, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    std::vector<int> k0(h.begin(), h.begin() + p->n0), k1(h.begin() + p->n0, h.begin() + p->n0 + p->n1);
+    kept_range(k0, p->n0, &p->keep0_lo, &p->keep0_hi);
+    kept_range(k1, p->n1, &p->keep1_lo, &p->keep1_hi);
+    int kx = 0;
+    for (int i = 0; i < p->nk; ++i)
+        if (h[p->n0 + p->n1 + i]) kx = i + 1;
+    p->keepx = kx > 0 ? kx : 1;
+    if (p->n0 == 1) { p->keep0_lo = 1; p->keep0_hi = 1; }
+    return 0;
+}
+
+// Dealias-pruned transforms: when on, the fused path visits only the bounding box of the modes the
+// dealiasing mask keeps (all other modes of the state, the tendencies and every intermediate are
+// exact zeros and are neither loaded, transformed nor stored).  Valid only when the state itself is
+// dealiased (true after every step); the host side switches it on accordingly.
+extern "C" int b2_set_pruning(b2_plan* p, int on) {
+    if (on && !p->mask) return b2i_set_error("b2_set_pruning: no dealiasing mask set");
+    if (on && p->slab) return b2i_set_error("b2_set_pruning: not implemented for slab plans");
+    p->prune = on ? 1 : 0;
+    return 0;
+}
+/* kept index ranges: out[0..4] = keep0_lo, keep0_hi, keep1_lo, keep1_hi, keepx */
+extern "C" int b2_get_pruning_bounds(const b2_plan* p, int* out) {
+    out[0] = p->keep0_lo; out[1] = p->keep0_hi; out[2] = p->keep1_lo; out[3] = p->keep1_hi; out[4] = p->keepx;
+    return 0;
+}
+
 extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4,
                               int has_f, double f, double N, double beta, const uint8_t* mask) {
     if (solver < 0 || solver > 2) return b2i_set_error("b2_set_physics: unknown solver %d", solver);
@@ -737,7 +834,12 @@ extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, do
     p->solver = solver;
     p->nu2 = nu2; p->nu4 = nu4; p->nu8 = nu8; p->num4 = num4;
     p->has_f = has_f; p->f = f; p->N = N; p->beta = beta;
+    const bool mask_changed = p->mask != mask;
     p->mask = mask;
+    if (mask_changed || !mask) {
+        p->prune = 0;
+        return compute_mask_bounds(p);
+    }
     return 0;
 }
 
@@ -784,7 +886,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
     constexpr int NV = SOLVER == B2_SOLVER_NS3D ? 3 : (SOLVER == B2_SOLVER_NS3D_STRAT ? 4 : 1);
     const KGrid& g = a.g;
     B2_ROW_SETUP
-    for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
         const double Kx = g.kx[ikx];
         const long long i = rbase + ikx;
         const bool origin = row_origin && ikx == 0;
@@ -896,7 +998,7 @@ static int launch_rk_stage_s(int mode, const RKArgs& a, unsigned grid, cudaStrea
 
 static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s) {
     ProfScope ps(PC_RK, s);
-    const unsigned grid = nrows(p);
+    const unsigned grid = nrows_fused(p);
     switch (p->solver) {
         case B2_SOLVER_NS3D: return launch_rk_stage_s<B2_SOLVER_NS3D>(mode, a, grid, s);
         case B2_SOLVER_NS3D_STRAT: return launch_rk_stage_s<B2_SOLVER_NS3D_STRAT>(mode, a, grid, s);
@@ -918,10 +1020,12 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
     const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
     const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
     int e;
+    const bool pr = p->prune != 0;
+    const int nkeep = pr ? p->keepx : p->nk;
     if (need_curl && p->solver != B2_SOLVER_NS2D) {
         ProfScope ps(PC_RK, s);
-        rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, s>>>(kgrid(p), in[0], in[1], in[2], W[3], W[4], W[5],
-                                                      p->has_f ? p->f : 0.0);
+        rot_kernel<<<nrows_fused(p), B2_ROW_THREADS, 0, s>>>(kgrid_fused(p), in[0], in[1], in[2], W[3], W[4],
+                                                            W[5], p->has_f ? p->f : 0.0);
         B2_LAUNCH_CHECK("rot_kernel");
     }
     {
@@ -930,19 +1034,19 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
     }
     if (p->n0 > 1) {
         ProfScope ps(PC_Y_INV, s);
-        if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s))) return e;
+        if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s, pr))) return e;
     }
     {
         ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, s))) return e;
+        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, s))) return e;
     }
     {
         ProfScope ps(PC_Y_FWD, s);
-        if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s))) return e;
+        if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s, pr))) return e;
     }
     if (p->n0 > 1) {
         ProfScope ps(PC_Z_FWD, s);
-        if ((e = b2i_strided_plain(p, 0, -1, Wc, W, nout, 1.0, s))) return e;
+        if ((e = b2i_strided_plain(p, 0, -1, Wc, W, nout, 1.0, s, pr))) return e;
     }
     return 0;
 }
@@ -960,7 +1064,7 @@ static int check_fused_ready(b2_plan* p, bool need_rk) {
 
 static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     RKArgs a;
-    a.g = kgrid(p);
+    a.g = kgrid_fused(p);
     a.visc = visc_of(p, p->nu2, p->nu4, p->nu8, p->num4);
     a.W = p->work;
     a.Sin = Sin;
@@ -1094,7 +1198,7 @@ extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
     }
     {
         ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, X, (long long)p->gy * p->nzl, scale, s))) return e;
+        if ((e = b2i_xpass_fused(p, X, (long long)p->gy * p->nzl, scale, p->nk, s))) return e;
     }
     ProfScope ps(PC_Y_FWD, s);
     return b2i_slab_ypass(p, -1, X, nout, s);

@@ -21,6 +21,9 @@ struct b2_plan {
     const uint8_t* mask;
     // caller-owned buffers (b2_set_buffers)
     cplx *acc, *stage, *work;
+    // dealias-pruned transforms (b2_set_pruning): kept index ranges per K axis, [0, lo) and [hi, n)
+    int prune;
+    int keep0_lo, keep0_hi, keep1_lo, keep1_hi, keepx;
     // slab decomposition (b2_plan_create_slab): the plan then describes the LOCAL K-layout array
     // (n0 = ny_loc, n1 = nz, n2 = nx; k0 = local ky, k1 = kz; tw1 = table of length nz)
     bool slab;
@@ -47,7 +50,7 @@ void b2i_count_launch();
 
 // --- strided passes (strided.cu).  axis: 0 (z, skipped when n0 == 1) or 1 (y).  dir: -1 fwd, +1 inv.
 int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx* const* out, int nf,
-                      double scale, cudaStream_t s);
+                      double scale, cudaStream_t s, bool pruned = false);
 // first inverse pass of a stage with the k-space prologue fused on load:
 //   ns3d / strat : in = nvar stage-input fields; out = W[0..2] = v, W[3..5] = curl v (+f), W[6] = b
 //   ns2d         : in = rot; out = W[0]=ux, W[1]=uy, W[2]=d_x rot, W[3]=d_y rot
@@ -57,7 +60,7 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 int b2i_xpass_c2r(b2_plan* p, const cplx* K, double* X, cudaStream_t s);
 int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream_t s);
 // fused c2r -> product -> r2c for p->solver; W fields as produced by b2i_first_inverse_pass
-int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, cudaStream_t s);
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, cudaStream_t s);
 
 // --- slab (multi-GPU) passes (strided.cu).  Exchange layout of one field: [peer r][ky_loc][z_loc][kx]
 // z pass between the local K layout (ny_loc, nz, nk) and the exchange layout:

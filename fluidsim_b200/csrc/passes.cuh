@@ -21,7 +21,23 @@ struct Geom {
     long long os;   // stride (elements) between outer batches
     long long cs;   // stride between columns (1 for the fast path)
     int nf;         // number of fields handled by the launch
+    // dealias-pruned transforms: the kept (non dealiased) wavenumbers of an axis are the index
+    // ranges [0, lo) and [lo + gap, n).  `outer` runs over the kept outer indices only and is
+    // mapped to memory by o -> o < outer_lo ? o : o + outer_gap.  Along the FFT axis the rows
+    // i in [band_lo, band_hi) are known zeros: they are not loaded (skip_load, inverse passes) or
+    // not stored (skip_store, forward passes).
+    int outer_lo, outer_gap;
+    int band_lo, band_hi;
+    int skip_load, skip_store;
+    int wide;       // prefer the wide-tile configuration (plane-strided lines)
 };
+static inline Geom geom_init() {
+    Geom g;
+    g.ncols = 0; g.nouter = 1; g.es = 0; g.os = 0; g.cs = 1; g.nf = 1;
+    g.outer_lo = 1 << 30; g.outer_gap = 0; g.band_lo = 0; g.band_hi = 0; g.skip_load = 0; g.skip_store = 0;
+    g.wide = 0;
+    return g;
+}
 
 #define B2_MAXF 8
 
@@ -59,21 +75,23 @@ __global__ void __launch_bounds__(TK*(N / E))
     // for different output fields (curl prologue) run at the same time and share it through L2
     const int field = blockIdx.x % g.nf;
     const int col = (blockIdx.x / g.nf) * TK + c;
-    const int outer = blockIdx.y;
+    const int outer = (int)blockIdx.y < g.outer_lo ? (int)blockIdx.y : (int)blockIdx.y + g.outer_gap;
     const bool active = col < g.ncols;
     const long long base = (long long)outer * g.os + col;
     cplx x[E];
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         const int i = t + m * T;
-        x[m] = active ? ld(field, base + (long long)i * g.es, i, col, outer) : make_double2(0.0, 0.0);
+        const bool zero = !active || (g.skip_load && i >= g.band_lo && i < g.band_hi);
+        x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)i * g.es, i, col, outer);
     }
     fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
     if (active) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int i = t + m * T;
-            st(field, base + (long long)i * g.es, i, col, outer, x[m]);
+            if (!(g.skip_store && i >= g.band_lo && i < g.band_hi))
+                st(field, base + (long long)i * g.es, i, col, outer, x[m]);
         }
     }
 }
@@ -94,13 +112,15 @@ struct PlainIn {
 // n = t + m*T.  Unnormalised (FFTW c2r convention).  Imaginary parts of k=0 and k=N/2 are ignored.
 template <int N, int E, class Sync>
 B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, cplx* plane, int t,
-                        const cplx* __restrict__ twN, Sync sync) {
+                        const cplx* __restrict__ twN, Sync sync, int nkeep) {
     constexpr int M = N / 2, T = M / E;
+    const cplx zero = make_double2(0.0, 0.0);
 #pragma unroll
     for (int m = 0; m < E; ++m) {
         const int k = t + m * T;
-        const cplx a = K[k];
-        const cplx b = K[M - k];
+        // modes k >= nkeep are dealiased zeros (never stored): not loaded
+        const cplx a = k < nkeep ? K[k] : zero;
+        const cplx b = M - k < nkeep ? K[M - k] : zero;
         if (k == 0) {
             x[m] = make_double2(a.x + b.x, a.x - b.x);
         } else {
@@ -118,7 +138,7 @@ B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, cplx* plane, i
 // r2c: x[m] = (u[2n], u[2n+1]) on entry; writes K[0..M] scaled by `scale`.
 template <int N, int E, class Sync>
 B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
-                        const cplx* __restrict__ twN, Sync sync, double scale, bool do_store) {
+                        const cplx* __restrict__ twN, Sync sync, double scale, bool do_store, int nkeep) {
     constexpr int M = N / 2, T = M / E;
     fft_line<M, E, -1, 1, 2>(x, plane, t, 0, twN, sync);
     sync();
@@ -132,7 +152,7 @@ B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
         if (k == 0) {
             if (do_store) {
                 K[0] = make_double2((x[m].x + x[m].y) * scale, 0.0);
-                K[M] = make_double2((x[m].x - x[m].y) * scale, 0.0);
+                if (M < nkeep) K[M] = make_double2((x[m].x - x[m].y) * scale, 0.0);
             }
         } else {
             const cplx zc = cconj(plane[b2_pad<1>(M - k)]);  // conj(Z[M-k])
@@ -140,7 +160,7 @@ B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
             const cplx d = csub(x[m], zc);
             const cplx w = __ldg(twN + k);
             const cplx e = cmul(d, w);
-            if (do_store) K[k] = make_double2((s.x + e.y) * hs, (s.y - e.x) * hs);
+            if (do_store && k < nkeep) K[k] = make_double2((s.x + e.y) * hs, (s.y - e.x) * hs);
         }
     }
 }
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     if (!active) line = nlines - 1;
     cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PS;
     cplx x[E];
-    c2r_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock());
+    c2r_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock(), M + 1);
     if (active) {
         double2* out = reinterpret_cast<double2*>(X + line * N);
 #pragma unroll
@@ -187,7 +207,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     const double2* in = reinterpret_cast<const double2*>(X + line * N);
 #pragma unroll
     for (int m = 0; m < E; ++m) x[m] = in[t + m * T];
-    r2c_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock(), scale, active);
+    r2c_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock(), scale, active, M + 1);
 }
 
 // fused: NI spectral lines -> c2r -> pointwise Op -> r2c -> NO spectral lines.
@@ -196,7 +216,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // Physical values are parked in thread-private shared-memory slots between transforms.
 template <int N, int E, int LPB, class Op>
 __global__ void __launch_bounds__(LPB*((N / 2) / E))
-    xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
+    xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
@@ -211,7 +231,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     cplx x[E];
 #pragma unroll 1
     for (int f = 0; f < NI; ++f) {
-        c2r_line<N, E>(x, op.in[f] + loff, plane, t, twN, SyncBlock());
+        c2r_line<N, E>(x, op.in[f] + loff, plane, t, twN, SyncBlock(), nkeep);
 #pragma unroll
         for (int m = 0; m < E; ++m) park[(f * E + m) * T + t] = x[m];
     }
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     for (int o = 0; o < NO; ++o) {
 #pragma unroll
         for (int m = 0; m < E; ++m) x[m] = park[(o * E + m) * T + t];
-        r2c_line<N, E>(x, op.out[o] + loff, plane, t, twN, SyncBlock(), scale, active);
+        r2c_line<N, E>(x, op.out[o] + loff, plane, t, twN, SyncBlock(), scale, active, nkeep);
     }
 }
 
@@ -247,7 +267,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // group g (chosen so that it uses the group's own register-resident field).
 template <int N, int E, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
-    xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale) {
+    xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
@@ -259,9 +279,9 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
     const long long loff = line * (M + 1);
     cplx x[E];
     if constexpr (T <= 32) {
-        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp());
+        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp(), nkeep);
     } else {
-        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1});
+        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, nkeep);
     }
 #pragma unroll
     for (int m = 0; m < E; ++m) park[(g * E + m) * T + t] = x[m];
@@ -283,9 +303,9 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E))
     }
     cplx* const outp = op.out[op.out_of_group(g)] + loff;
     if constexpr (T <= 32) {
-        r2c_line<N, E>(x, outp, plane, t, twN, SyncWarp(), scale, true);
+        r2c_line<N, E>(x, outp, plane, t, twN, SyncWarp(), scale, true, nkeep);
     } else {
-        r2c_line<N, E>(x, outp, plane, t, twN, SyncNamed<T>{g + 1}, scale, true);
+        r2c_line<N, E>(x, outp, plane, t, twN, SyncNamed<T>{g + 1}, scale, true, nkeep);
     }
 }
 
@@ -302,12 +322,13 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     extern __shared__ double b2_smem[];
     cplx* a = reinterpret_cast<cplx*>(b2_smem);
     cplx* b = a + (size_t)N * TK;
-    const int outer = blockIdx.y, field = blockIdx.z;
+    const int outer = (int)blockIdx.y < g.outer_lo ? (int)blockIdx.y : (int)blockIdx.y + g.outer_gap;
+    const int field = blockIdx.z;
     const int col0 = blockIdx.x * TK;
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
         cplx v = make_double2(0.0, 0.0);
-        if (col < g.ncols)
+        if (col < g.ncols && !(g.skip_load && i >= g.band_lo && i < g.band_hi))
             v = ld(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer);
         a[idx] = v;
     }
@@ -342,7 +363,7 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     }
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
-        if (col < g.ncols)
+        if (col < g.ncols && !(g.skip_store && i >= g.band_lo && i < g.band_hi))
             st(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer,
                a[idx]);
     }

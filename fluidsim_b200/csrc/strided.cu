@@ -85,7 +85,7 @@ static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStre
     if constexpr (N == 1024) {
         // measured (profiles/r1_tuning.md): the plane-strided z pass wants 128-byte row segments
         // (TK = 8, one 512-thread CTA per SM), the y pass prefers two 256-thread CTAs (TK = 4)
-        const bool zlike = g.nouter == 1;
+        const bool zlike = g.nouter == 1 || g.wide;
         switch (strided_variant()) {
             case 1: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
             case 2: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
@@ -117,8 +117,34 @@ static int launch_strided(bool fast, int N, Geom g, int nf, In in, S st, const c
     return launch_generic<DIR>(N, g, nf, ld, st, tw, s);
 }
 
+// pruned geometries: only kept kx columns / kept outer rows are visited, the dealiased band of the
+// transformed axis is skipped on load (inverse) or on store (forward)
+static Geom geom_pruned(const b2_plan* p, int axis, int dir) {
+    Geom g = geom_init();
+    g.ncols = p->keepx;
+    if (axis == 0) {  // z pass over kept (ky, kx) columns
+        g.nouter = p->keep1_lo + (p->n1 - p->keep1_hi);
+        g.outer_lo = p->keep1_lo;
+        g.outer_gap = p->keep1_hi - p->keep1_lo;
+        g.es = (long long)p->n1 * p->nk;
+        g.os = p->nk;
+        g.band_lo = p->keep0_lo;
+        g.band_hi = p->keep0_hi;
+        g.wide = 1;
+    } else {  // y pass over kept kx columns, all z
+        g.nouter = p->n0;
+        g.es = p->nk;
+        g.os = (long long)p->n1 * p->nk;
+        g.band_lo = p->keep1_lo;
+        g.band_hi = p->keep1_hi;
+    }
+    g.skip_load = dir > 0;
+    g.skip_store = dir < 0;
+    return g;
+}
+
 static Geom geom_for_axis(const b2_plan* p, int axis) {
-    Geom g;
+    Geom g = geom_init();
     if (axis == 0) {  // z pass: columns = flattened (i1, kx)
         g.ncols = p->n1 * p->nk;  // < 2^31 for all supported sizes
         g.nouter = 1;
@@ -136,10 +162,10 @@ static Geom geom_for_axis(const b2_plan* p, int axis) {
 }
 
 int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx* const* out, int nf,
-                      double scale, cudaStream_t s) {
+                      double scale, cudaStream_t s, bool pruned) {
     if (axis == 0 && p->n0 == 1) return 0;
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
-    Geom g = geom_for_axis(p, axis);
+    Geom g = pruned ? geom_pruned(p, axis, dir) : geom_for_axis(p, axis);
     const int N = axis == 0 ? p->n0 : p->n1;
     const bool fast = axis == 0 ? p->fast0 : p->fast1;
     const cplx* tw = axis == 0 ? p->tw0 : p->tw1;
@@ -192,7 +218,8 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
         ld.kx = p->kx;
         PlainStore st;
         for (int f = 0; f < 4; ++f) st.out[f] = out[f];
-        return launch_strided<+1>(p->fast1, p->n1, geom_for_axis(p, 1), 4, ld, st, p->tw1, s);
+        return launch_strided<+1>(p->fast1, p->n1, p->prune ? geom_pruned(p, 1, +1) : geom_for_axis(p, 1), 4, ld,
+                                  st, p->tw1, s);
     }
     const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
     const int nout = nv + 3;
@@ -204,7 +231,8 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
     if (nv == 4) ld.in[6] = in[3];
     const int axis = p->n0 > 1 ? 0 : 1;
     return launch_strided<+1>(axis == 0 ? p->fast0 : p->fast1, axis == 0 ? p->n0 : p->n1,
-                              geom_for_axis(p, axis), nout, ld, st, axis == 0 ? p->tw0 : p->tw1, s);
+                              p->prune ? geom_pruned(p, axis, +1) : geom_for_axis(p, axis), nout, ld, st,
+                              axis == 0 ? p->tw0 : p->tw1, s);
 }
 
 // ------------------------------------------------------------------------------- slab passes
@@ -236,12 +264,11 @@ struct SlabIn {
 
 int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
-    Geom g;
+    Geom g = geom_init();
     g.ncols = p->nk;
     g.nouter = p->n0;  // ny_loc
     g.es = p->nk;
     g.os = (long long)p->n1 * p->nk;
-    g.cs = 1;
     g.nf = nf;
     const SlabMapper map{p->nzl, p->nyl, p->nk};
     if (dir > 0) {
@@ -260,12 +287,9 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
 
 int b2i_slab_ypass(b2_plan* p, int dir, cplx* const* bufs, int nf, cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
-    Geom g;
+    Geom g = geom_init();
     g.ncols = p->nzl * p->nk;
-    g.nouter = 1;
     g.es = (long long)p->nzl * p->nk;
-    g.os = 0;
-    g.cs = 1;
     g.nf = nf;
     PlainIn ld;
     PlainStore st;

@@ -40,6 +40,10 @@ class SimulBasePseudoSpectralB200:
         self._init_projection()
         self._fused_buffers = None
         self._fused_mask = None
+        # dealias-pruned transforms: used for a step only when the state is known to be dealiased
+        # (true after every step; reset by state.mark_spect_modified()).
+        self.use_pruning = True
+        self._state_dealiased = False
         self.time_stepping = self.TimeStepping(self, fused=fused)
 
     def _init_projection(self):
@@ -83,6 +87,7 @@ class SimulBasePseudoSpectralB200:
     def tendencies_nonlin_fused(self, state_spect=None, old=None):
         """N(state_spect) through the fused kernels (C ABI ``b2_tendencies``)."""
         self._ensure_fused_buffers()
+        call("b2_set_pruning", self.oper.plan.handle, 0)  # arbitrary input: no assumption on zeros
         src = self.state.state_spect if state_spect is None else state_spect
         tendencies_fft = SetOfVariables(like=self.state.state_spect, info="tendencies_nonlin") if old is None else old
         call("b2_tendencies", self.oper.plan.handle, ptr(src.tensor), ptr(tendencies_fft.tensor), stream_ptr())

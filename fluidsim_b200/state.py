@@ -53,7 +53,10 @@ class StatePseudoSpectral:
         return self._state_phys
 
     def mark_spect_modified(self):
+        """Call after writing ``state_spect`` from outside the time stepper: invalidates the lazy
+        ``state_phys`` and the "state is dealiased" knowledge the pruned transforms rely on."""
         self._phys_dirty = True
+        self.sim._state_dealiased = False
 
     def statephys_from_statespect(self):
         """base/state.py:326-332 -- deferred until ``state_phys`` is read."""

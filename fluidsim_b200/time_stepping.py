@@ -184,6 +184,8 @@ class TimeSteppingPseudoSpectralB200:
         state_spect = sim.state.state_spect
         if self.fused:
             sim._ensure_fused_buffers()
+            prune = sim.use_pruning and sim._state_dealiased and sim._fused_mask is not None
+            call("b2_set_pruning", sim.oper.plan.handle, 1 if prune else 0)
             call(
                 "b2_time_step", sim.oper.plan.handle, self._scheme_id, float(self.deltat),
                 ptr(state_spect.tensor), stream_ptr(),
@@ -194,6 +196,7 @@ class TimeSteppingPseudoSpectralB200:
                 sim.project_state_spect(state_spect)
             sim.oper.dealiasing(state_spect)
         sim.state.statephys_from_statespect()
+        sim._state_dealiased = True  # every step ends with oper.dealiasing(state_spect)
         if self.check_nan_period and (self.it + 1) % self.check_nan_period == 0:
             call("b2_sum", ptr(state_spect.tensor), 2 * state_spect.tensor[0].numel(), ptr(self._maxbuf), stream_ptr())
             if torch.isnan(self._maxbuf).item():

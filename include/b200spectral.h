@@ -122,6 +122,12 @@ int b2_sum(const double* x, long long n, double* out_dev, void* stream);
  * mask = where_dealiased (uint8, K-shaped, device; may be NULL = no dealiasing) */
 int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4, int has_f,
                    double f, double N, double beta, const uint8_t* mask);
+/* dealias-pruned transforms: with on != 0 the fused path visits only the bounding box of the modes
+ * kept by the mask (exact: everything outside is zero).  Requires the state to be dealiased, which
+ * holds after every step (solvers/ns3d/time_stepping.py:16); off by default. */
+int b2_set_pruning(b2_plan* p, int on);
+/* out[0..4] = kept ranges [0,out[0]) U [out[1],n0), [0,out[2]) U [out[3],n1), kx < out[4] */
+int b2_get_pruning_bounds(const b2_plan* p, int* out);
 /* number of K-sized complex work fields the fused path needs for this solver (W), nvar of state */
 int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar);
 /* caller-owned buffers: acc, stage (each nvar K-fields), work (nwork K-fields) */

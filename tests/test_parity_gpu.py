@@ -267,3 +267,39 @@ def test_nan_raises_value_error():
     sim.state.state_spect.tensor[0, 1, 1, 1] = float("nan")
     with pytest.raises(ValueError, match="nan at it"):
         sim.time_stepping.one_time_step()
+
+
+# ------------------------------------------------------------------ dealias-pruned transforms
+@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "ns2d_32x32_rk4"])
+def test_pruned_steps_match_golden_and_unpruned(name):
+    """From the second step on the fused path skips everything outside the bounding box of the
+    kept modes; results must be unchanged (the skipped data are exact zeros)."""
+    meta, z = load_golden(name)
+    sims = []
+    for use_pruning in (True, False):
+        sim = make_gpu_sim(meta, fused=True, mask=z["mask"])
+        sim.use_pruning = use_pruning
+        set_state(sim, z["state0"])
+        for _ in range(meta["nsteps"]):
+            sim.time_stepping.one_time_step()
+        sims.append(sim)
+    a, b = sims[0].state.state_spect.numpy(), sims[1].state.state_spect.numpy()
+    assert rel_err(a, z["stateN"]) < 10 * TOL_STEP
+    assert rel_err(a, b) < 1e-13
+    # the pruned path was really used, and the dealiased region is exactly zero
+    import ctypes as C
+
+    from fluidsim_b200._lib import lib
+
+    bounds = (C.c_int * 5)()
+    lib.b2_get_pruning_bounds(sims[0].oper.plan.handle, bounds)
+    assert bounds[4] < sims[0].oper.shapeK_loc[-1]
+    assert np.abs(a[:, z["mask"].astype(bool)]).max() == 0.0
+
+
+def test_pruned_128_taylor_green_and_noise():
+    for init in ("init_taylor_green", "init_noise"):
+        meta = dict(solver="ns3d", shape=(64, 128, 32), params=dict(nu_2=1e-3, deltat0=5e-3, Lx=3.0))
+        o, sim, worst = _run_both(meta, 6, init)
+        assert sim._state_dealiased
+        assert worst < 1e-10
