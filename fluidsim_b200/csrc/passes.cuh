@@ -265,8 +265,8 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // the latency hiding of this pass needs (see profiles/).
 // Op additionally provides out_of_group(g), needs(g, f) and point_g(g, u): the output formed by
 // group g (chosen so that it uses the group's own register-resident field).
-template <int N, int E, class Op>
-__global__ void __launch_bounds__(Op::NI*((N / 2) / E))
+template <int N, int E, int MINB, class Op>
+__global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;

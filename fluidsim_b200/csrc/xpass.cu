@@ -1,4 +1,6 @@
 // Contiguous-axis (x) passes: c2r, r2c and the fused c2r -> physical-space product -> r2c kernel.
+#include <stdlib.h>
+
 #include "internal.h"
 #include "passes.cuh"
 
@@ -123,7 +125,7 @@ template <int N, class Op>
 static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
-    auto kern = xpass_fused_fp_kernel<N, E, Op>;
+    auto kern = getenv("B2_XMINB") ? xpass_fused_fp_kernel<N, E, 2, Op> : xpass_fused_fp_kernel<N, E, 1, Op>;
     static bool attr_done = false;
     if (!attr_done) {
         if (smem > 48 * 1024)
