@@ -264,8 +264,7 @@ def make_slab_sim(args, torch, dist):
     c = 2.0 / 3
     lim = c * dk * (n // 2 + 1)
     mask = ((ky >= lim)[:, None, None] | (kz >= lim)[None, :, None] | (kx >= lim)[None, None, :])
-    sim.where_dealiased = mask.to(torch.uint8).contiguous()
-    sim._push()
+    sim.set_local_mask(mask.to(torch.uint8))
     g = torch.Generator(device=dev).manual_seed(42 + sim.rank)
     S = sim.state_spect
     k0 = 2 * math.pi / (2 * math.pi / 4.0)

@@ -69,6 +69,7 @@ SIGNATURES = {
     "b2_time_step": [_p, _i, _d, _p, _p],
     "b2_plan_create_slab": [C.POINTER(_p), _i, _i, _i, _d, _d, _d, _i, _i],
     "b2_slab_set_buffers": [_p, _p, _p],
+    "b2_slab_set_pruning": [_p, _i, _i, _i, _i, _i, _i, _i, _i],
     "b2_slab_phase_a": [_p, _p, _i, _p],
     "b2_slab_phase_b": [_p, _p],
     "b2_slab_phase_c": [_p, _i, _i, _d, _p, _p, _p, _p],

@@ -770,15 +770,16 @@ __global__ void mask_bounds_kernel(const uint8_t* mask, int n0, int n1, int nk, 
 }
 
 static void kept_range(const std::vector<int>& keep, int n, int* lo, int* hi) {
-    // kept indices are contained in [0, lo) U [hi, n)
-    int l = 0, h = n;
-    for (int i = 0; i <= n / 2 && i < n; ++i)
-        if (keep[i]) l = i + 1;
-    for (int i = n - 1; i > n / 2; --i)
-        if (keep[i]) h = i;
-    if (h < l) h = l;
-    *lo = l;
-    *hi = h;
+    // [lo, hi) = smallest index interval containing every fully dealiased index, so that the kept
+    // indices are contained in [0, lo) U [hi, n)
+    int first = -1, last = -1;
+    for (int i = 0; i < n; ++i)
+        if (!keep[i]) {
+            if (first < 0) first = i;
+            last = i;
+        }
+    if (first < 0) { *lo = n; *hi = n; }
+    else { *lo = first; *hi = last + 1; }
 }
 
 static int compute_mask_bounds(b2_plan* p) {
@@ -813,8 +814,30 @@ static int compute_mask_bounds(b2_plan* p) {
 // dealiased (true after every step); the host side switches it on accordingly.
 extern "C" int b2_set_pruning(b2_plan* p, int on) {
     if (on && !p->mask) return b2i_set_error("b2_set_pruning: no dealiasing mask set");
-    if (on && p->slab) return b2i_set_error("b2_set_pruning: not implemented for slab plans");
+    if (on && p->slab) return b2i_set_error("b2_set_pruning: use b2_slab_set_pruning on slab plans");
     p->prune = on ? 1 : 0;
+    return 0;
+}
+// Slab plans: the kept ranges must be agreed between the ranks (host side, fluidsim_b200/slab.py):
+// kx < keepx and the kz band [kz_lo, kz_hi) are global; [yl_lo, yl_hi) is the dealiased band of the
+// LOCAL ky rows; [gy_lo, gy_hi) the dealiased band of the global ky index (y passes on the z-slab
+// side).  Only the kept local ky rows / kx columns are exchanged.
+extern "C" int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int yl_lo, int yl_hi,
+                                   int gy_lo, int gy_hi) {
+    if (!p->slab) return b2i_set_error("b2_slab_set_pruning: not a slab plan");
+    if (!on) {
+        p->prune = 0;
+        return 0;
+    }
+    if (!p->mask) return b2i_set_error("b2_slab_set_pruning: no dealiasing mask set");
+    if (keepx < 1 || keepx > p->nk || kz_lo > kz_hi || kz_hi > p->n1 || yl_lo > yl_hi || yl_hi > p->n0 ||
+        gy_lo > gy_hi || gy_hi > p->gy)
+        return b2i_set_error("b2_slab_set_pruning: inconsistent ranges");
+    p->keepx = keepx;
+    p->keep1_lo = kz_lo; p->keep1_hi = kz_hi;
+    p->keep0_lo = yl_lo; p->keep0_hi = yl_hi;
+    p->gyk_lo = gy_lo; p->gyk_hi = gy_hi;
+    p->prune = 1;
     return 0;
 }
 /* kept index ranges: out[0..4] = keep0_lo, keep0_hi, keep1_lo, keep1_hi, keepx */
@@ -999,6 +1022,7 @@ static int launch_rk_stage_s(int mode, const RKArgs& a, unsigned grid, cudaStrea
 static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s) {
     ProfScope ps(PC_RK, s);
     const unsigned grid = nrows_fused(p);
+    if (grid == 0) return 0;
     switch (p->solver) {
         case B2_SOLVER_NS3D: return launch_rk_stage_s<B2_SOLVER_NS3D>(mode, a, grid, s);
         case B2_SOLVER_NS3D_STRAT: return launch_rk_stage_s<B2_SOLVER_NS3D_STRAT>(mode, a, grid, s);
@@ -1038,7 +1062,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
     }
     {
         ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, s))) return e;
+        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, p->nk, s))) return e;
     }
     {
         ProfScope ps(PC_Y_FWD, s);
@@ -1164,11 +1188,11 @@ extern "C" int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, vo
     const cplx* Sin = (const cplx*)S_in;
     const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
     const int nin = nv + 3;
-    if (need_curl) {
+    if (need_curl && nrows_fused(p) > 0) {
         ProfScope ps(PC_RK, s);
-        rot_kernel<<<nrows(p), B2_ROW_THREADS, 0, s>>>(kgrid(p), Sin, Sin + fs, Sin + 2 * fs, p->work + 3 * fs,
-                                                      p->work + 4 * fs, p->work + 5 * fs,
-                                                      p->has_f ? p->f : 0.0);
+        rot_kernel<<<nrows_fused(p), B2_ROW_THREADS, 0, s>>>(kgrid_fused(p), Sin, Sin + fs, Sin + 2 * fs,
+                                                            p->work + 3 * fs, p->work + 4 * fs,
+                                                            p->work + 5 * fs, p->has_f ? p->f : 0.0);
         B2_LAUNCH_CHECK("rot_kernel");
     }
     const cplx* in[8];
@@ -1189,19 +1213,28 @@ extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
     const long long fs = p->fsize();
     const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
     const int nin = nv + 3, nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
-    cplx* X[8];
-    for (int f = 0; f < nin; ++f) X[f] = p->xb + f * fs;
+    // unpruned: everything in place on xb.  pruned: y-inverse expands xb (kept ky rows) into xa
+    // (all ny rows), the x pass works in place on xa, y-forward compacts xa back into xb.
+    cplx* XB[8];
+    cplx* XW[8];
+    const cplx* XBc[8];
+    const cplx* XWc[8];
+    for (int f = 0; f < nin; ++f) {
+        XBc[f] = XB[f] = p->xb + f * fs;
+        XWc[f] = XW[f] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+    }
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
+    const int pitch = p->prune ? p->keepx : p->nk;
     {
         ProfScope ps(PC_Y_INV, s);
-        if ((e = b2i_slab_ypass(p, +1, X, nin, s))) return e;
+        if ((e = b2i_slab_ypass(p, +1, XBc, XW, nin, s))) return e;
     }
     {
         ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, X, (long long)p->gy * p->nzl, scale, p->nk, s))) return e;
+        if ((e = b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, s))) return e;
     }
     ProfScope ps(PC_Y_FWD, s);
-    return b2i_slab_ypass(p, -1, X, nout, s);
+    return b2i_slab_ypass(p, -1, XWc, XB, nout, s);
 }
 
 // phase C: z-forward from the receive buffers xa into work[0..nout-1], then the RK epilogue.

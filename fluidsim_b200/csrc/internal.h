@@ -33,6 +33,7 @@ struct b2_plan {
     bool fasty;
     cplx* twy;     // table of length gy
     cplx *xa, *xb; // exchange buffers (b2_slab_set_buffers), nwork fields each
+    int gyk_lo, gyk_hi;  // global dealiased ky band (pruned slab y passes)
     long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
     long long xsize() const { return (long long)n0 * n1 * n2; }
 };
@@ -60,7 +61,8 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 int b2i_xpass_c2r(b2_plan* p, const cplx* K, double* X, cudaStream_t s);
 int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream_t s);
 // fused c2r -> product -> r2c for p->solver; W fields as produced by b2i_first_inverse_pass
-int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, cudaStream_t s);
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch,
+                    cudaStream_t s);
 
 // --- slab (multi-GPU) passes (strided.cu).  Exchange layout of one field: [peer r][ky_loc][z_loc][kx]
 // z pass between the local K layout (ny_loc, nz, nk) and the exchange layout:
@@ -68,4 +70,4 @@ int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, 
 //   dir = -1 (forward): in = exchange-layout receive buffers, out = K-layout fields
 int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s);
 // y pass in place on receive buffers viewed as (ny, nz_loc, nk)
-int b2i_slab_ypass(b2_plan* p, int dir, cplx* const* bufs, int nf, cudaStream_t s);
+int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s);

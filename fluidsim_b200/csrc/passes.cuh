@@ -30,12 +30,16 @@ struct Geom {
     int band_lo, band_hi;
     int skip_load, skip_store;
     int wide;       // prefer the wide-tile configuration (plane-strided lines)
+    // compact row storage: row i of the line lives at memory row (i < lo ? i : i - gap) of the
+    // source (ld_*) / destination (st_*) array (band rows are never touched)
+    int ld_lo, ld_gap, st_lo, st_gap;
 };
 static inline Geom geom_init() {
     Geom g;
     g.ncols = 0; g.nouter = 1; g.es = 0; g.os = 0; g.cs = 1; g.nf = 1;
     g.outer_lo = 1 << 30; g.outer_gap = 0; g.band_lo = 0; g.band_hi = 0; g.skip_load = 0; g.skip_store = 0;
     g.wide = 0;
+    g.ld_lo = 1 << 30; g.ld_gap = 0; g.st_lo = 1 << 30; g.st_gap = 0;
     return g;
 }
 
@@ -83,15 +87,17 @@ __global__ void __launch_bounds__(TK*(N / E))
     for (int m = 0; m < E; ++m) {
         const int i = t + m * T;
         const bool zero = !active || (g.skip_load && i >= g.band_lo && i < g.band_hi);
-        x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)i * g.es, i, col, outer);
+        const int il = i < g.ld_lo ? i : i - g.ld_gap;
+        x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)il * g.es, i, col, outer);
     }
     fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
     if (active) {
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int i = t + m * T;
+            const int is = i < g.st_lo ? i : i - g.st_gap;
             if (!(g.skip_store && i >= g.band_lo && i < g.band_hi))
-                st(field, base + (long long)i * g.es, i, col, outer, x[m]);
+                st(field, base + (long long)is * g.es, i, col, outer, x[m]);
         }
     }
 }
@@ -216,7 +222,8 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // Physical values are parked in thread-private shared-memory slots between transforms.
 template <int N, int E, int LPB, class Op>
 __global__ void __launch_bounds__(LPB*((N / 2) / E))
-    xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep) {
+    xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
+                       int pitch) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     if (!active) line = nlines - 1;
     cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PER_LS;
     cplx* park = plane + PS;
-    const long long loff = line * (M + 1);
+    const long long loff = line * pitch;
     cplx x[E];
 #pragma unroll 1
     for (int f = 0; f < NI; ++f) {
@@ -267,7 +274,8 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // group g (chosen so that it uses the group's own register-resident field).
 template <int N, int E, int MINB, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
-    xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep) {
+    xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
+                          int pitch) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
@@ -276,7 +284,7 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     const long long line = blockIdx.x;
     cplx* park = reinterpret_cast<cplx*>(b2_smem);    // [NI][E][T] complex
     cplx* plane = park + (size_t)NI * M + (size_t)g * PS;  // per-group exchange plane
-    const long long loff = line * (M + 1);
+    const long long loff = line * pitch;
     cplx x[E];
     if constexpr (T <= 32) {
         c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp(), nkeep);
@@ -328,8 +336,9 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
         cplx v = make_double2(0.0, 0.0);
+        const int il = i < g.ld_lo ? i : i - g.ld_gap;
         if (col < g.ncols && !(g.skip_load && i >= g.band_lo && i < g.band_hi))
-            v = ld(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer);
+            v = ld(field, (long long)outer * g.os + (long long)il * g.es + (long long)col * g.cs, i, col, outer);
         a[idx] = v;
     }
     __syncthreads();
@@ -363,8 +372,9 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     }
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
+        const int is = i < g.st_lo ? i : i - g.st_gap;
         if (col < g.ncols && !(g.skip_store && i >= g.band_lo && i < g.band_hi))
-            st(field, (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs, i, col, outer,
+            st(field, (long long)outer * g.os + (long long)is * g.es + (long long)col * g.cs, i, col, outer,
                a[idx]);
     }
 }

@@ -237,13 +237,15 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 
 // ------------------------------------------------------------------------------- slab passes
 // Index map between K-layout coordinates (yl = outer, z = i, kx = col) and the exchange layout
-// [peer r = z / nzl][yl][zl = z % nzl][kx] of one field.
+// [peer q = z / nzl][kept local ky row][zl = z % nzl][kx < pitch] of one field.  With pruning only
+// the kept local ky rows (compact index) and the kept kx columns are exchanged.
 struct SlabMapper {
-    int nzl, nyl, nk;
+    int nzl, nkl, pitch, y_lo, y_gap;
     B2_DEVINL long long operator()(int z, int kx, int yl) const {
-        const int r = z / nzl;
-        const int zl = z - r * nzl;
-        return (((long long)r * nyl + yl) * nzl + zl) * nk + kx;
+        const int q = z / nzl;
+        const int zl = z - q * nzl;
+        const int ylc = yl < y_lo ? yl : yl - y_gap;
+        return (((long long)q * nkl + ylc) * nzl + zl) * pitch + kx;
     }
 };
 struct SlabStore {
@@ -265,12 +267,27 @@ struct SlabIn {
 int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
     Geom g = geom_init();
-    g.ncols = p->nk;
-    g.nouter = p->n0;  // ny_loc
     g.es = p->nk;
     g.os = (long long)p->n1 * p->nk;
     g.nf = nf;
-    const SlabMapper map{p->nzl, p->nyl, p->nk};
+    SlabMapper map;
+    map.nzl = p->nzl;
+    if (p->prune) {
+        g.ncols = p->keepx;
+        g.nouter = p->keep0_lo + (p->n0 - p->keep0_hi);  // kept local ky rows
+        g.outer_lo = p->keep0_lo;
+        g.outer_gap = p->keep0_hi - p->keep0_lo;
+        g.band_lo = p->keep1_lo;  // kz band
+        g.band_hi = p->keep1_hi;
+        g.skip_load = dir > 0;
+        g.skip_store = dir < 0;
+        map.nkl = g.nouter; map.pitch = p->keepx; map.y_lo = p->keep0_lo; map.y_gap = g.outer_gap;
+    } else {
+        g.ncols = p->nk;
+        g.nouter = p->n0;
+        map.nkl = p->n0; map.pitch = p->nk; map.y_lo = 1 << 30; map.y_gap = 0;
+    }
+    if (g.nouter == 0) return 0;  // this rank owns only dealiased ky rows
     if (dir > 0) {
         PlainIn ld;
         SlabStore st;
@@ -285,15 +302,26 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     return launch_strided<-1>(p->fast1, p->n1, g, nf, ld, st, p->tw1, s);
 }
 
-int b2i_slab_ypass(b2_plan* p, int dir, cplx* const* bufs, int nf, cudaStream_t s) {
+// y pass on the z-slab side.  Unpruned: in place on (ny, nz_loc, nk).  Pruned: the exchanged array
+// holds only the kept ky rows (compact) and kx < keepx columns; the inverse pass expands it to all
+// ny rows (in -> out), the forward pass stores the kept rows back in compact form.
+int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
     Geom g = geom_init();
-    g.ncols = p->nzl * p->nk;
-    g.es = (long long)p->nzl * p->nk;
+    const int pitch = p->prune ? p->keepx : p->nk;
+    g.ncols = p->nzl * pitch;
+    g.es = (long long)p->nzl * pitch;
     g.nf = nf;
+    g.wide = 1;
+    if (p->prune) {
+        g.band_lo = p->gyk_lo;
+        g.band_hi = p->gyk_hi;
+        if (dir > 0) { g.skip_load = 1; g.ld_lo = p->gyk_lo; g.ld_gap = p->gyk_hi - p->gyk_lo; }
+        else { g.skip_store = 1; g.st_lo = p->gyk_lo; g.st_gap = p->gyk_hi - p->gyk_lo; }
+    }
     PlainIn ld;
     PlainStore st;
-    for (int f = 0; f < nf; ++f) { ld.in[f] = bufs[f]; st.out[f] = bufs[f]; }
+    for (int f = 0; f < nf; ++f) { ld.in[f] = in[f]; st.out[f] = out[f]; }
     return dir < 0 ? launch_strided<-1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s)
                    : launch_strided<+1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s);
 }

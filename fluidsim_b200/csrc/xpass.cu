@@ -122,7 +122,7 @@ static int launch_r2c_n(const double* X, cplx* K, long long nlines, const cplx* 
 }
 
 template <int N, class Op>
-static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, cudaStream_t s) {
+static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
     auto kern = getenv("B2_XMINB") ? xpass_fused_fp_kernel<N, E, 2, Op> : xpass_fused_fp_kernel<N, E, 1, Op>;
@@ -132,17 +132,17 @@ static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double sca
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    kern<<<(unsigned)nlines, Op::NI * T, smem, s>>>(op, nlines, tw, scale, nkeep);
+    kern<<<(unsigned)nlines, Op::NI * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch);
     B2_LAUNCH_CHECK("xpass_fused_fp_kernel");
     return 0;
 }
 
 template <int N, class Op>
-static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, cudaStream_t s) {
+static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem_fp = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
     if constexpr ((T % 32 == 0 || (T == 16 && (Op::NI * T) % 32 == 0)) && smem_fp <= 227 * 1024)
-        return launch_fused_fp_n<N>(op, nlines, tw, scale, nkeep, s);
+        return launch_fused_fp_n<N>(op, nlines, tw, scale, nkeep, pitch, s);
     constexpr size_t per_ls = ((size_t)PlaneSize<M, 1>::value + (size_t)Op::NI * M) * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
@@ -155,7 +155,7 @@ static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale,
         attr_done = true;
     }
     const unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);
-    kern<<<grid, LPB * T, smem, s>>>(op, nlines, tw, scale, nkeep);
+    kern<<<grid, LPB * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch);
     B2_LAUNCH_CHECK("xpass_fused_kernel");
     return 0;
 }
@@ -255,32 +255,32 @@ int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream
 }
 
 template <class Op>
-static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int nkeep, cudaStream_t s) {
+static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int nkeep, int pitch, cudaStream_t s) {
     switch (p->n2) {
-#define B2_CASE(n) case n: return launch_fused_n<n>(op, nlines, p->tw2, scale, nkeep, s);
+#define B2_CASE(n) case n: return launch_fused_n<n>(op, nlines, p->tw2, scale, nkeep, pitch, s);
         B2_XSIZES(B2_CASE)
 #undef B2_CASE
     }
     return b2i_set_error("fused x pass: nx=%d not supported (power of two in [8, 2048])", p->n2);
 }
 
-int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, cudaStream_t s) {
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch, cudaStream_t s) {
     if (!p->fast2) return b2i_set_error("fused x pass needs a power-of-two nx");
     if (p->solver == B2_SOLVER_NS3D) {
         OpNS3D op;
         for (int f = 0; f < 6; ++f) op.in[f] = W[f];
         for (int f = 0; f < 3; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, nlines, scale, nkeep, s);
+        return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
     }
     if (p->solver == B2_SOLVER_NS3D_STRAT) {
         OpStrat op;
         for (int f = 0; f < 7; ++f) op.in[f] = W[f];
         for (int f = 0; f < 6; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, nlines, scale, nkeep, s);
+        return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
     }
     OpNS2D op;
     for (int f = 0; f < 4; ++f) op.in[f] = W[f];
     op.out[0] = W[0];
     op.beta = p->beta;
-    return launch_fused(p, op, nlines, scale, nkeep, s);
+    return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
 }

@@ -102,6 +102,10 @@ class SlabSimul:
         self.it = 0
         self.t = 0.0
         self._scalar = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # dealias-pruned exchange (set up by set_mask...; used once the state is known dealiased)
+        self.use_pruning = True
+        self._state_dealiased = False
+        self._prune = None
         self._push()
 
     def _push(self):
@@ -119,12 +123,71 @@ class SlabSimul:
     def set_mask_from_global(self, mask_global):
         """``where_dealiased`` of the sequential operator ``(nz, ny, nk)`` -> local slab."""
         loc = local_from_global(np.asarray(mask_global, dtype=np.uint8), self.rank, self.world)
-        self.where_dealiased = self.torch.from_numpy(loc).to(self.device)
+        self.set_local_mask(self.torch.from_numpy(loc).to(self.device))
+
+    def set_local_mask(self, mask_local):
+        self.where_dealiased = mask_local.contiguous()
         self._push()
+        self._setup_pruning()
 
     def set_state_from_global(self, state_global):
         loc = local_from_global(np.asarray(state_global), self.rank, self.world)
         self.state_spect.copy_(self.torch.from_numpy(loc))
+        self._state_dealiased = False
+
+    def mark_spect_modified(self):
+        self._state_dealiased = False
+
+    # ---- pruning set-up -----------------------------------------------------------------------------
+    @staticmethod
+    def _band(keep):
+        """[lo, hi): smallest index interval containing every non-kept index (kept_range in api.cu)."""
+        idx = np.nonzero(~np.asarray(keep, dtype=bool))[0]
+        n = len(keep)
+        return (n, n) if idx.size == 0 else (int(idx[0]), int(idx[-1]) + 1)
+
+    def _setup_pruning(self):
+        """Agree on the kept ranges between the ranks and derive the all-to-all split sizes."""
+        tr, dist = self.torch, self.dist
+        if self.where_dealiased is None:
+            self._prune = None
+            return
+        kept = self.where_dealiased == 0  # (ny_loc, nz, nk)
+        kx = kept.any(dim=0).any(dim=0).to(tr.int32)
+        kz = kept.any(dim=2).any(dim=0).to(tr.int32)
+        kyl = kept.any(dim=2).any(dim=1).to(tr.int32)
+        dist.all_reduce(kx, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(kz, op=dist.ReduceOp.MAX, group=self.group)
+        parts = [tr.empty_like(kyl) for _ in range(self.world)]
+        dist.all_gather(parts, kyl, group=self.group)
+        kx, kz, kyl = kx.cpu().numpy(), kz.cpu().numpy(), kyl.cpu().numpy()
+        kyg = np.concatenate([p.cpu().numpy() for p in parts])
+        keepx = int(np.nonzero(kx)[0].max()) + 1 if kx.any() else 1
+        kz_lo, kz_hi = self._band(kz)
+        gy_lo, gy_hi = self._band(kyg)
+        # local band = intersection of the global band with this rank's rows (keeps the layouts of
+        # all ranks consistent with the global compact ky index)
+        a = self.rank * self.nyl
+        yl_lo = min(max(gy_lo - a, 0), self.nyl)
+        yl_hi = min(max(gy_hi - a, 0), self.nyl)
+        if yl_hi <= yl_lo:
+            yl_lo = yl_hi = self.nyl
+        nkl = []
+        for r in range(self.world):
+            a_r = r * self.nyl
+            lo = min(max(gy_lo - a_r, 0), self.nyl)
+            hi = min(max(gy_hi - a_r, 0), self.nyl)
+            nkl.append(self.nyl - max(hi - lo, 0))
+        blk = self.nzl * keepx * 2  # float64 elements per kept ky row
+        self._prune = dict(
+            args=(keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi),
+            nkl=nkl,
+            # inverse exchange (K side -> z-slab side): equal blocks out, per-peer row counts in
+            inv_in=[nkl[self.rank] * blk] * self.world,
+            inv_out=[n * blk for n in nkl],
+            fwd_in=[n * blk for n in nkl],
+            fwd_out=[nkl[self.rank] * blk] * self.world,
+        )
 
     def gather_state(self):
         """Global sequential-layout state on every rank (testing / small grids only)."""
@@ -133,22 +196,33 @@ class SlabSimul:
         return global_from_local([p.cpu().numpy() for p in parts])
 
     # ---- collectives ------------------------------------------------------------------------------
-    def _all_to_all(self, src, dst, nf):
-        """Per field: ``world`` equal contiguous blocks (NCCL over NVLink; gloo on CPU tests)."""
+    def _all_to_all(self, src, dst, nf, splits=None):
+        """Per field: one contiguous block per peer (NCCL over NVLink; gloo on CPU tests).  Unpruned:
+        ``world`` equal blocks covering the whole field; pruned: only the kept ky rows x kx columns,
+        ``splits = (input_split_sizes, output_split_sizes)`` in float64 elements."""
         tr = self.torch
         for f in range(nf):
-            self.dist.all_to_all_single(tr.view_as_real(dst[f]).view(-1), tr.view_as_real(src[f]).view(-1),
-                                        group=self.group)
+            d, s_ = tr.view_as_real(dst[f]).view(-1), tr.view_as_real(src[f]).view(-1)
+            if splits is None:
+                self.dist.all_to_all_single(d, s_, group=self.group)
+            else:
+                ins, outs = splits
+                self.dist.all_to_all_single(d[: sum(outs)], s_[: sum(ins)], outs, ins, group=self.group)
 
     # ---- stepping ---------------------------------------------------------------------------------
-    def _run_stage(self, Sin, need_curl, scheme_id, stage, tout=None):
+    def _run_stage(self, Sin, need_curl, scheme_id, stage, tout=None, prune=False):
         from ._lib import call, ptr, stream_ptr
 
         h = self.handle
+        pr = self._prune if (prune and self._prune is not None) else None
+        if pr is None:
+            call("b2_slab_set_pruning", h, 0, 0, 0, 0, 0, 0, 0, 0)
+        else:
+            call("b2_slab_set_pruning", h, 1, *pr["args"])
         call("b2_slab_phase_a", h, ptr(Sin), 1 if need_curl else 0, stream_ptr())
-        self._all_to_all(self._xa, self._xb, self.nwork)
+        self._all_to_all(self._xa, self._xb, self.nwork, None if pr is None else (pr["inv_in"], pr["inv_out"]))
         call("b2_slab_phase_b", h, stream_ptr())
-        self._all_to_all(self._xb, self._xa, self.nout)
+        self._all_to_all(self._xb, self._xa, self.nout, None if pr is None else (pr["fwd_in"], pr["fwd_out"]))
         call("b2_slab_phase_c", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout),
              stream_ptr())
 
@@ -161,9 +235,11 @@ class SlabSimul:
     def one_time_step(self):
         sid = SCHEME_IDS[self.scheme]
         nstages = 4 if self.scheme == "RK4" else 2
+        prune = self.use_pruning and self._state_dealiased
         for st in range(nstages):
             Sin = self.state_spect if st == 0 else self._stagebuf
-            self._run_stage(Sin, st == 0, sid, st)
+            self._run_stage(Sin, st == 0, sid, st, prune=prune)
+        self._state_dealiased = True  # the last stage projects and dealiases the state
         self.t += self.deltat
         self.it += 1
 

@@ -148,6 +148,10 @@ int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
 int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx, int rank,
                         int nranks);
 int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb);
+/* pruned exchange (see b2_set_pruning): kept ranges agreed between the ranks by the host side; the
+ * all-to-alls then carry only the kept local ky rows x kx < keepx (uneven splits) */
+int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int yl_lo, int yl_hi,
+                        int gy_lo, int gy_hi);
 int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream);
 int b2_slab_phase_b(b2_plan* p, void* stream);
 /* stage < 0: tendencies only (written to T_out); else stage of `scheme`, updating acc/stage/S */

@@ -47,7 +47,8 @@ def _worker(rank, world, port, name, q):
         from fluidsim_b200.slab import global_from_local
 
         e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts]), z["tend0"])
-        sim.one_time_step()
+        sim.one_time_step()  # unpruned (state not known to be dealiased)
+        assert sim._prune is not None
         e_1 = rel_err(sim.gather_state(), z["state1"])
         for _ in range(meta["nsteps"] - 1):
             sim.one_time_step()
