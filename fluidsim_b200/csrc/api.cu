@@ -1178,88 +1178,152 @@ static int slab_ready(b2_plan* p) {
     return 0;
 }
 
-// phase A: (first stage: vorticity of Sin -> work[3..5]); z-inverse of v, omega, [b] into the send
-// buffers xa (exchange layout)
-extern "C" int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream) {
+// Fine-grained stage pieces (field ranges [f0, f1)) so that the host side can pipeline the
+// per-field all-to-alls with the FFT passes of the other fields.
+extern "C" int b2_slab_curl(b2_plan* p, const double* S_in, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e;
     if ((e = slab_ready(p))) return e;
     const long long fs = p->fsize();
     const cplx* Sin = (const cplx*)S_in;
-    const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
-    const int nin = nv + 3;
-    if (need_curl && nrows_fused(p) > 0) {
-        ProfScope ps(PC_RK, s);
-        rot_kernel<<<nrows_fused(p), B2_ROW_THREADS, 0, s>>>(kgrid_fused(p), Sin, Sin + fs, Sin + 2 * fs,
-                                                            p->work + 3 * fs, p->work + 4 * fs,
-                                                            p->work + 5 * fs, p->has_f ? p->f : 0.0);
-        B2_LAUNCH_CHECK("rot_kernel");
-    }
-    const cplx* in[8];
-    cplx* out[8];
-    for (int f = 0; f < 3; ++f) in[f] = Sin + f * fs;
-    for (int f = 3; f < 6; ++f) in[f] = p->work + f * fs;
-    if (nv == 4) in[6] = Sin + 3 * fs;
-    for (int f = 0; f < nin; ++f) out[f] = p->xa + f * fs;
-    ProfScope ps(PC_FIRST_INV, s);
-    return b2i_slab_zpass(p, +1, in, out, nin, s);
+    if (nrows_fused(p) == 0) return 0;
+    ProfScope ps(PC_RK, s);
+    rot_kernel<<<nrows_fused(p), B2_ROW_THREADS, 0, s>>>(kgrid_fused(p), Sin, Sin + fs, Sin + 2 * fs,
+                                                        p->work + 3 * fs, p->work + 4 * fs, p->work + 5 * fs,
+                                                        p->has_f ? p->f : 0.0);
+    B2_LAUNCH_CHECK("rot_kernel");
+    return 0;
 }
 
-// phase B: y-inverse, fused x pass, y-forward, in place on the receive buffers xb
-extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
-    int e;
-    if ((e = slab_ready(p))) return e;
-    const long long fs = p->fsize();
+static int slab_counts(b2_plan* p, int* nin, int* nout) {
     const int nv = p->solver == B2_SOLVER_NS3D_STRAT ? 4 : 3;
-    const int nin = nv + 3, nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
-    // unpruned: everything in place on xb.  pruned: y-inverse expands xb (kept ky rows) into xa
-    // (all ny rows), the x pass works in place on xa, y-forward compacts xa back into xb.
-    cplx* XB[8];
-    cplx* XW[8];
-    const cplx* XBc[8];
-    const cplx* XWc[8];
-    for (int f = 0; f < nin; ++f) {
-        XBc[f] = XB[f] = p->xb + f * fs;
-        XWc[f] = XW[f] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+    *nin = nv + 3;
+    *nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
+    return nv;
+}
+
+// z-inverse of work-field slots [f0, f1) (0..2 = v from S_in, 3..5 = omega from work, 6 = b) -> xa
+extern "C" int b2_slab_zinv(b2_plan* p, const double* S_in, int f0, int f1, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if (f0 < 0 || f1 > nin || f0 >= f1) return b2i_set_error("b2_slab_zinv: bad field range");
+    const long long fs = p->fsize();
+    const cplx* Sin = (const cplx*)S_in;
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = f0; f < f1; ++f) {
+        in[f - f0] = f < 3 ? Sin + f * fs : (f < 6 ? p->work + f * fs : Sin + 3 * fs);
+        out[f - f0] = p->xa + f * fs;
     }
+    ProfScope ps(PC_FIRST_INV, s);
+    return b2i_slab_zpass(p, +1, in, out, f1 - f0, s);
+}
+
+// y-inverse of fields [f0, f1): xb -> (pruned: xa expanded | unpruned: xb in place)
+extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if (f0 < 0 || f1 > nin || f0 >= f1) return b2i_set_error("b2_slab_yinv: bad field range");
+    const long long fs = p->fsize();
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = f0; f < f1; ++f) {
+        in[f - f0] = p->xb + f * fs;
+        out[f - f0] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+    }
+    ProfScope ps(PC_Y_INV, s);
+    return b2i_slab_ypass(p, +1, in, out, f1 - f0, s);
+}
+
+extern "C" int b2_slab_xpass(b2_plan* p, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    const long long fs = p->fsize();
+    cplx* XW[8];
+    for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * fs : p->xb + f * fs;
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
     const int pitch = p->prune ? p->keepx : p->nk;
-    {
-        ProfScope ps(PC_Y_INV, s);
-        if ((e = b2i_slab_ypass(p, +1, XBc, XW, nin, s))) return e;
-    }
-    {
-        ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, s))) return e;
-    }
-    ProfScope ps(PC_Y_FWD, s);
-    return b2i_slab_ypass(p, -1, XWc, XB, nout, s);
+    ProfScope ps(PC_X_FUSED, s);
+    return b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, s);
 }
 
-// phase C: z-forward from the receive buffers xa into work[0..nout-1], then the RK epilogue.
-// scheme/stage select the update (stage < 0: tendencies only, written to T_out).
-extern "C" int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S_,
-                               double* T_out, void* stream) {
+// y-forward of output fields [f0, f1): (pruned: xa -> xb compact | unpruned: xb in place)
+extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if (f0 < 0 || f1 > nout || f0 >= f1) return b2i_set_error("b2_slab_yfwd: bad field range");
+    const long long fs = p->fsize();
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = f0; f < f1; ++f) {
+        in[f - f0] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+        out[f - f0] = p->xb + f * fs;
+    }
+    ProfScope ps(PC_Y_FWD, s);
+    return b2i_slab_ypass(p, -1, in, out, f1 - f0, s);
+}
+
+// z-forward of output fields [f0, f1): xa (exchange layout) -> work (K layout)
+extern "C" int b2_slab_zfwd(b2_plan* p, int f0, int f1, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if (f0 < 0 || f1 > nout || f0 >= f1) return b2i_set_error("b2_slab_zfwd: bad field range");
+    const long long fs = p->fsize();
+    const cplx* in[8];
+    cplx* out[8];
+    for (int f = f0; f < f1; ++f) { in[f - f0] = p->xa + f * fs; out[f - f0] = p->work + f * fs; }
+    ProfScope ps(PC_Z_FWD, s);
+    return b2i_slab_zpass(p, -1, in, out, f1 - f0, s);
+}
+
+// RK epilogue on work[0..nout-1] (stage < 0: tendencies only, written to T_out)
+extern "C" int b2_slab_rk(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S_,
+                          double* T_out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e;
     if ((e = slab_ready(p))) return e;
-    const long long fs = p->fsize();
-    const int nout = p->solver == B2_SOLVER_NS3D ? 3 : 6;
-    const cplx* in[8];
-    cplx* out[8];
-    for (int f = 0; f < nout; ++f) { in[f] = p->xa + f * fs; out[f] = p->work + f * fs; }
-    {
-        ProfScope ps(PC_Z_FWD, s);
-        if ((e = b2i_slab_zpass(p, -1, in, out, nout, s))) return e;
-    }
     int mode;
     if (stage < 0) mode = M_TEND;
     else if (scheme == B2_SCHEME_RK4 && stage < 4) mode = M_RK4_0 + stage;
     else if (scheme == B2_SCHEME_RK2 && stage < 2) mode = M_RK2_0 + stage;
-    else return b2i_set_error("b2_slab_phase_c: bad scheme/stage %d/%d", scheme, stage);
+    else return b2i_set_error("b2_slab_rk: bad scheme/stage %d/%d", scheme, stage);
     if (mode != M_TEND && (!p->acc || !p->stage)) return b2i_set_error("b2_set_buffers: acc/stage missing");
     RKArgs a = rk_args(p, (const cplx*)S_in, (cplx*)S_, dt);
     a.Tout = (cplx*)T_out;
     return launch_rk_stage(p, mode, a, s);
+}
+
+// Coarse phases (A, B, C) = the pieces above without pipelining.
+extern "C" int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream) {
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if (need_curl && (e = b2_slab_curl(p, S_in, stream))) return e;
+    return b2_slab_zinv(p, S_in, 0, nin, stream);
+}
+extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if ((e = b2_slab_yinv(p, 0, nin, stream))) return e;
+    if ((e = b2_slab_xpass(p, stream))) return e;
+    return b2_slab_yfwd(p, 0, nout, stream);
+}
+extern "C" int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S_,
+                               double* T_out, void* stream) {
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    slab_counts(p, &nin, &nout);
+    if ((e = b2_slab_zfwd(p, 0, nout, stream))) return e;
+    return b2_slab_rk(p, scheme, stage, dt, S_in, S_, T_out, stream);
 }

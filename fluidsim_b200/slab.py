@@ -104,6 +104,7 @@ class SlabSimul:
         self._scalar = torch.zeros(1, dtype=torch.float64, device=self.device)
         # dealias-pruned exchange (set up by set_mask...; used once the state is known dealiased)
         self.use_pruning = True
+        self.pipelined = True  # overlap the per-field all-to-alls with the FFT passes
         self._state_dealiased = False
         self._prune = None
         self._push()
@@ -209,6 +210,15 @@ class SlabSimul:
                 ins, outs = splits
                 self.dist.all_to_all_single(d[: sum(outs)], s_[: sum(ins)], outs, ins, group=self.group)
 
+    def _all_to_all_async(self, src, dst, splits):
+        tr = self.torch
+        d, s_ = tr.view_as_real(dst).view(-1), tr.view_as_real(src).view(-1)
+        if splits is None:
+            return self.dist.all_to_all_single(d, s_, group=self.group, async_op=True)
+        ins, outs = splits
+        return self.dist.all_to_all_single(d[: sum(outs)], s_[: sum(ins)], outs, ins, group=self.group,
+                                           async_op=True)
+
     # ---- stepping ---------------------------------------------------------------------------------
     def _run_stage(self, Sin, need_curl, scheme_id, stage, tout=None, prune=False):
         from ._lib import call, ptr, stream_ptr
@@ -219,12 +229,42 @@ class SlabSimul:
             call("b2_slab_set_pruning", h, 0, 0, 0, 0, 0, 0, 0, 0)
         else:
             call("b2_slab_set_pruning", h, 1, *pr["args"])
-        call("b2_slab_phase_a", h, ptr(Sin), 1 if need_curl else 0, stream_ptr())
-        self._all_to_all(self._xa, self._xb, self.nwork, None if pr is None else (pr["inv_in"], pr["inv_out"]))
-        call("b2_slab_phase_b", h, stream_ptr())
-        self._all_to_all(self._xb, self._xa, self.nout, None if pr is None else (pr["fwd_in"], pr["fwd_out"]))
-        call("b2_slab_phase_c", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout),
-             stream_ptr())
+        inv = None if pr is None else (pr["inv_in"], pr["inv_out"])
+        fwd = None if pr is None else (pr["fwd_in"], pr["fwd_out"])
+        if not self.pipelined:
+            call("b2_slab_phase_a", h, ptr(Sin), 1 if need_curl else 0, stream_ptr())
+            self._all_to_all(self._xa, self._xb, self.nwork, inv)
+            call("b2_slab_phase_b", h, stream_ptr())
+            self._all_to_all(self._xb, self._xa, self.nout, fwd)
+            call("b2_slab_phase_c", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect),
+                 ptr(tout), stream_ptr())
+            return
+        # pipelined: the all-to-all of field f runs on NCCL's stream while the FFT passes of the
+        # neighbouring fields run on the compute stream
+        sp = stream_ptr()
+        order = list(range(self.nwork))
+        if need_curl:  # v (and b) first: they do not depend on the curl kernel
+            order = [0, 1, 2] + list(range(6, self.nwork)) + [3, 4, 5]
+        works = {}
+        curl_done = not need_curl
+        for f in order:
+            if not curl_done and 3 <= f < 6:
+                call("b2_slab_curl", h, ptr(Sin), sp)
+                curl_done = True
+            call("b2_slab_zinv", h, ptr(Sin), f, f + 1, sp)
+            works[f] = self._all_to_all_async(self._xa[f], self._xb[f], inv)
+        for f in order:
+            works[f].wait()
+            call("b2_slab_yinv", h, f, f + 1, sp)
+        call("b2_slab_xpass", h, sp)
+        works = {}
+        for f in range(self.nout):
+            call("b2_slab_yfwd", h, f, f + 1, sp)
+            works[f] = self._all_to_all_async(self._xb[f], self._xa[f], fwd)
+        for f in range(self.nout):
+            works[f].wait()
+            call("b2_slab_zfwd", h, f, f + 1, sp)
+        call("b2_slab_rk", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout), sp)
 
     def tendencies_nonlin(self, state_spect=None, old=None):
         src = self.state_spect if state_spect is None else state_spect

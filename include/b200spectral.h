@@ -152,6 +152,17 @@ int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb);
  * all-to-alls then carry only the kept local ky rows x kx < keepx (uneven splits) */
 int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int yl_lo, int yl_hi,
                         int gy_lo, int gy_hi);
+/* fine-grained pieces over work-field ranges [f0, f1) -- lets the host pipeline the per-field
+ * all-to-alls with the FFT passes of the other fields (fluidsim_b200/slab.py) */
+int b2_slab_curl(b2_plan* p, const double* S_in, void* stream);
+int b2_slab_zinv(b2_plan* p, const double* S_in, int f0, int f1, void* stream);
+int b2_slab_yinv(b2_plan* p, int f0, int f1, void* stream);
+int b2_slab_xpass(b2_plan* p, void* stream);
+int b2_slab_yfwd(b2_plan* p, int f0, int f1, void* stream);
+int b2_slab_zfwd(b2_plan* p, int f0, int f1, void* stream);
+int b2_slab_rk(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S, double* T_out,
+               void* stream);
+/* coarse phases = the same pieces, all fields at once */
 int b2_slab_phase_a(b2_plan* p, const double* S_in, int need_curl, void* stream);
 int b2_slab_phase_b(b2_plan* p, void* stream);
 /* stage < 0: tendencies only (written to T_out); else stage of `scheme`, updating acc/stage/S */
