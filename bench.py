@@ -27,14 +27,34 @@ UNIT = "grid-pts*steps/s"
 
 # algorithmic HBM bytes, in field passes F = 16*n0*n1*(n2/2+1) bytes
 STEP_PASSES = {("ns3d", "RK4"): 195, ("ns3d.strat", "RK4"): 282, ("ns2d", "RK4"): 57, ("ns3d", "RK2"): 90}
-# per-launch field passes of each kernel class of the fused path (ns3d): read + written fields
-CLASS_NAMES = ["first_inverse_pass_curl", "y_inverse", "x_fused_c2r_cross_r2c", "y_forward", "z_forward",
+CLASS_NAMES = ["first_inverse_pass", "y_inverse", "x_fused_c2r_cross_r2c", "y_forward", "z_forward",
                "rk_project_dealias_epilogue"]
-CLASS_PASSES = {
-    "ns3d": [3 + 6, 6 + 6, 6 + 3, 3 + 3, 3 + 3, (12 + 15 + 15 + 9) / 4.0 + 1 / 16.0],
-    "ns3d.strat": [4 + 7, 7 + 7, 7 + 6, 6 + 6, 6 + 6, (18 + 22 + 22 + 14) / 4.0 + 1 / 16.0],
-    "ns2d": [1 + 4, 0, 4 + 1, 1 + 1, 0, (4 + 5 + 5 + 3) / 4.0 + 1 / 16.0],
-}
+SOLVER_COUNTS = {"ns3d": (3, 6, 3), "ns3d.strat": (4, 7, 6), "ns2d": (1, 4, 1)}  # nvar, n_in, n_out
+
+
+def class_passes(solver, fx=1.0, fy=1.0, fz=1.0):
+    """Algorithmic field passes (read + written, unit F) per LAUNCH of each kernel class of the fused
+    path as built.  fx, fy, fz = kept fraction of kx columns / ky rows / kz
+    rows (dealias-pruned transforms; 1 = unpruned).  ns2d has no z passes (fz = 1)."""
+    nvar, nin, nout = SOLVER_COUNTS[solver]
+    box = fx * fy * fz
+    if solver == "ns2d":
+        first = 1 * fx * fy + nin * fx          # y-inverse with the ns2d prologue: R rot (kept), W 4
+        return [first, 0.0, nin * fx + nout * fx, nout * fx + nout * fx * fy, 0.0,
+                ((2 + 2) + (3 + 2) + (3 + 2) + (2 + 1)) / 4.0 * box + box / 16.0]
+    first = nin * box + nin * fx * fy            # z-inverse: R kept box, W all z of kept columns
+    yinv = nin * fx * fy + nin * fx
+    xp = nin * fx + nout * fx
+    yfwd = nout * fx + nout * fx * fy
+    zfwd = nout * fx * fy + nout * box
+    extra = 2 if solver == "ns3d.strat" else 0   # b and vz of the stage input (buoyancy coupling)
+    # RK epilogue, averaged over the 4 stages (+ the stage-0 curl kernel R3 W3): reads raw T (nout),
+    # S, acc; writes acc, next stage input, its vorticity (3)
+    # (5 launches per RK4 step in this class: the stage-0 curl kernel + 4 epilogues)
+    rk = ((nout + nvar + extra) + (2 * nvar + 3) + 6
+          + 2 * ((nout + 2 * nvar + extra) + (2 * nvar + 3))
+          + ((nout + nvar + extra) + nvar)) / 5.0 * box + box / 16.0
+    return [first, yinv, xp, yfwd, zfwd, rk]
 
 
 def parse_args():
@@ -344,6 +364,19 @@ def own_arm(args):
     if not bool(torch.isfinite(S.real.sum()).item()):
         raise RuntimeError("state became non finite during the benchmark")
 
+    # kept fractions of the dealias-pruned transforms actually used in the timed steps
+    kept = (1.0, 1.0, 1.0)
+    if world == 1 and sim.use_pruning and sim._fused_mask is not None:
+        import ctypes as C0
+
+        bnd = (C0.c_int * 5)()
+        _lib.lib.b2_get_pruning_bounds(sim.oper.plan.handle, bnd)
+        n0, n1, nk = (1,) * (3 - ndim) + tuple(sim.oper.shapeK_loc)
+        kept = (bnd[4] / nk, (bnd[2] + n1 - bnd[3]) / n1, (bnd[0] + n0 - bnd[1]) / n0)
+    elif world > 1 and sim.use_pruning and sim._prune is not None:
+        keepx, kz_lo, kz_hi, _, _, gy_lo, gy_hi = sim._prune["args"]
+        kept = (keepx / sim.nk, (gy_lo + sim.ny - gy_hi) / sim.ny, (kz_lo + sim.nz - kz_hi) / sim.nz)
+
     # ---- per-kernel-class timing (CUDA events on the launching stream inside the library)
     roofline = None
     classes = {}
@@ -363,7 +396,7 @@ def own_arm(args):
         cnt = (C.c_longlong * 6)()
         _lib.lib.b2_profile_get(msarr, cnt, 6)
         _lib.lib.b2_profile_enable(0)
-        passes = CLASS_PASSES[args.solver]
+        passes = class_passes(args.solver, *kept)
         tot = sum(msarr)
         best = None
         for i, name in enumerate(CLASS_NAMES):
@@ -376,10 +409,16 @@ def own_arm(args):
             if best is None or msarr[i] > msarr[best]:
                 best = i
         bname = CLASS_NAMES[best]
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this
+        # configuration (profiles/r1_ncu_xpass_1024_raw.csv: dram read 35.14 GB + write 17.23 GB)
+        traffic = 52.37e9 if (bname == "x_fused_c2r_cross_r2c" and args.n == 1024 and world == 1
+                              and args.solver == "ns3d") else None
         roofline = {"bound": "hbm", "kernel": bname, "achieved": classes[bname]["alg_GBps"], "peak": hbm_peak,
-                    "unit": "GB/s", "frac": classes[bname]["frac"], "traffic": None,
+                    "unit": "GB/s", "frac": classes[bname]["frac"], "traffic": traffic,
                     "peak_source": peak_src,
-                    "alg_bytes_per_launch": passes[best] * F}
+                    "alg_bytes_per_launch": passes[best] * F,
+                    "note": "algorithmic bytes of the launch as built (dealias-pruned: kept kx fraction "
+                            f"{kept[0]:.3f}, ky {kept[1]:.3f}, kz {kept[2]:.3f})"}
     barrier()
 
     # ---- end to end through the public API with HOST buffers (state in pinned host memory)
@@ -413,6 +452,16 @@ def own_arm(args):
                                   f"pocketfft oracle port, {r['ms_per_step']:.0f} ms/step"}
 
     if rank == 0:
+        nst = 4 if args.scheme == "RK4" else 2
+        cp = class_passes(args.solver, *kept)
+        built_passes = nst * sum(cp[:5]) + (5 if args.solver != "ns2d" else 4) * cp[5] if args.scheme == "RK4" else None
+        as_built = None
+        if built_passes:
+            bb = built_passes * F
+            as_built = {"kept_fraction_kx_ky_kz": kept, "field_passes_per_step": built_passes,
+                        "alg_bytes_per_step_per_gpu": bb,
+                        "achieved_GBps": bb / (ms_per_step * 1e-3) / 1e9,
+                        "frac": bb / (ms_per_step * 1e-3) / 1e9 / hbm_peak}
         step_passes = STEP_PASSES.get((args.solver, args.scheme))
         step_alg = step_passes * F if step_passes else None  # per GPU (F is the local field pass)
         nfft = {"ns3d": 36, "ns3d.strat": 52}.get(args.solver, 0) if args.scheme == "RK4" else 0
@@ -447,11 +496,13 @@ def own_arm(args):
             "nvlink": nvlink,
             "roofline": roofline,
             "step_roofline": {
+                "model": "SURVEY.md section 8d fused 3-pass model (unpruned)",
                 "model_field_passes": step_passes,
                 "alg_bytes_per_step": step_alg,
                 "achieved_GBps": step_alg / (ms_per_step * 1e-3) / 1e9 if step_alg else None,
                 "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / hbm_peak if step_alg else None,
             },
+            "step_traffic_as_built": as_built,
             "kernel_classes": classes,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e if e2e is not None else ({"note": e2e_note} if e2e_note else None),
