@@ -1031,6 +1031,35 @@ static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s
     return b2i_set_error("physics not set");
 }
 
+// number of z chunks of the overlapped y-inverse / x / y-forward section (1 = sequential).
+// Tuning knob: B2_NCHUNK (0 or 1 disables the overlap).
+static int overlap_chunks(const b2_plan* p) {
+    static int req = -1;
+    if (req < 0) {
+        const char* e = getenv("B2_NCHUNK");
+        req = e ? atoi(e) : 1;  // measured slower than the sequential passes (profiles/r1_tuning.md)
+    }
+    if (req <= 1 || p->n0 < 64 || p->n2 < 512) return 1;
+    int n = req > 32 ? 32 : req;
+    while (n > 1 && p->n0 / n < 8) n /= 2;
+    return n;
+}
+
+static int ensure_streams(b2_plan* p) {
+    if (p->streams_ready) return 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->sy1, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->sx, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->sy2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_begin, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&p->ev_end, cudaEventDisableTiming));
+    for (int i = 0; i < 32; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_y[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_x[i], cudaEventDisableTiming));
+    }
+    p->streams_ready = true;
+    return 0;
+}
+
 // raw nonlinear term of stage input `Sin` into work[0..nout-1] (scaled FFT, not yet projected)
 static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream_t s) {
     int nwork, nvar;
@@ -1056,17 +1085,53 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
         ProfScope ps(PC_FIRST_INV, s);
         if ((e = b2i_first_inverse_pass(p, in, W, s))) return e;
     }
-    if (p->n0 > 1) {
-        ProfScope ps(PC_Y_INV, s);
-        if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s, pr))) return e;
-    }
-    {
-        ProfScope ps(PC_X_FUSED, s);
-        if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, p->nk, s))) return e;
-    }
-    {
-        ProfScope ps(PC_Y_FWD, s);
-        if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s, pr))) return e;
+    const int nchunk = overlap_chunks(p);
+    if (nchunk > 1) {
+        // The x pass is bound by the L1 / FP64 pipes, the y passes by HBM: run them concurrently on
+        // different z chunks (three streams, one x-pass CTA + one y-pass CTA co-resident per SM).
+        if ((e = ensure_streams(p))) return e;
+        CUDA_TRY(cudaEventRecord(p->ev_begin, s));
+        CUDA_TRY(cudaStreamWaitEvent(p->sy1, p->ev_begin, 0));
+        CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_begin, 0));
+        CUDA_TRY(cudaStreamWaitEvent(p->sy2, p->ev_begin, 0));
+        b2i_xpass_share_sm(true);
+        for (int c = 0; c < nchunk; ++c) {
+            const int z0 = (int)((long long)p->n0 * c / nchunk), z1 = (int)((long long)p->n0 * (c + 1) / nchunk);
+            {
+                ProfScope ps(PC_Y_INV, p->sy1);
+                if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, p->sy1, pr, z0, z1 - z0))) return e;
+            }
+            CUDA_TRY(cudaEventRecord(p->ev_y[c], p->sy1));
+            CUDA_TRY(cudaStreamWaitEvent(p->sx, p->ev_y[c], 0));
+            {
+                ProfScope ps(PC_X_FUSED, p->sx);
+                if ((e = b2i_xpass_fused(p, W, (long long)(z1 - z0) * p->n1, scale, nkeep, p->nk,
+                                         (long long)z0 * p->n1, p->sx)))
+                    return e;
+            }
+            CUDA_TRY(cudaEventRecord(p->ev_x[c], p->sx));
+            CUDA_TRY(cudaStreamWaitEvent(p->sy2, p->ev_x[c], 0));
+            {
+                ProfScope ps(PC_Y_FWD, p->sy2);
+                if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, p->sy2, pr, z0, z1 - z0))) return e;
+            }
+        }
+        b2i_xpass_share_sm(false);
+        CUDA_TRY(cudaEventRecord(p->ev_end, p->sy2));
+        CUDA_TRY(cudaStreamWaitEvent(s, p->ev_end, 0));
+    } else {
+        if (p->n0 > 1) {
+            ProfScope ps(PC_Y_INV, s);
+            if ((e = b2i_strided_plain(p, 1, +1, Wc, W, nwork, 1.0, s, pr))) return e;
+        }
+        {
+            ProfScope ps(PC_X_FUSED, s);
+            if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, p->nk, 0, s))) return e;
+        }
+        {
+            ProfScope ps(PC_Y_FWD, s);
+            if ((e = b2i_strided_plain(p, 1, -1, Wc, W, nout, 1.0, s, pr))) return e;
+        }
     }
     if (p->n0 > 1) {
         ProfScope ps(PC_Z_FWD, s);
@@ -1250,7 +1315,7 @@ extern "C" int b2_slab_xpass(b2_plan* p, void* stream) {
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
     const int pitch = p->prune ? p->keepx : p->nk;
     ProfScope ps(PC_X_FUSED, s);
-    return b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, s);
+    return b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, 0, s);
 }
 
 // y-forward of output fields [f0, f1): (pruned: xa -> xb compact | unpruned: xb in place)

@@ -32,6 +32,10 @@ struct b2_plan {
     int nyl, nzl;  // ny / nranks, nz / nranks
     bool fasty;
     cplx* twy;     // table of length gy
+    // chunked y/x/y overlap (api.cu): side streams and events, created on first use
+    cudaStream_t sy1, sx, sy2;
+    cudaEvent_t ev_begin, ev_end, ev_y[32], ev_x[32];
+    bool streams_ready;
     cplx *xa, *xb; // exchange buffers (b2_slab_set_buffers), nwork fields each
     int gyk_lo, gyk_hi;  // global dealiased ky band (pruned slab y passes)
     long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
@@ -51,7 +55,7 @@ void b2i_count_launch();
 
 // --- strided passes (strided.cu).  axis: 0 (z, skipped when n0 == 1) or 1 (y).  dir: -1 fwd, +1 inv.
 int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx* const* out, int nf,
-                      double scale, cudaStream_t s, bool pruned = false);
+                      double scale, cudaStream_t s, bool pruned = false, int outer0 = 0, int nouter = -1);
 // first inverse pass of a stage with the k-space prologue fused on load:
 //   ns3d / strat : in = nvar stage-input fields; out = W[0..2] = v, W[3..5] = curl v (+f), W[6] = b
 //   ns2d         : in = rot; out = W[0]=ux, W[1]=uy, W[2]=d_x rot, W[3]=d_y rot
@@ -62,7 +66,8 @@ int b2i_xpass_c2r(b2_plan* p, const cplx* K, double* X, cudaStream_t s);
 int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream_t s);
 // fused c2r -> product -> r2c for p->solver; W fields as produced by b2i_first_inverse_pass
 int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch,
-                    cudaStream_t s);
+                    long long line0, cudaStream_t s);
+void b2i_xpass_share_sm(bool on);
 
 // --- slab (multi-GPU) passes (strided.cu).  Exchange layout of one field: [peer r][ky_loc][z_loc][kx]
 // z pass between the local K layout (ny_loc, nz, nk) and the exchange layout:

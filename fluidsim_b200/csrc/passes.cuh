@@ -33,6 +33,7 @@ struct Geom {
     // compact row storage: row i of the line lives at memory row (i < lo ? i : i - gap) of the
     // source (ld_*) / destination (st_*) array (band rows are never touched)
     int ld_lo, ld_gap, st_lo, st_gap;
+    int outer0;     // first outer index of this launch (chunked launches)
 };
 static inline Geom geom_init() {
     Geom g;
@@ -40,6 +41,7 @@ static inline Geom geom_init() {
     g.outer_lo = 1 << 30; g.outer_gap = 0; g.band_lo = 0; g.band_hi = 0; g.skip_load = 0; g.skip_store = 0;
     g.wide = 0;
     g.ld_lo = 1 << 30; g.ld_gap = 0; g.st_lo = 1 << 30; g.st_gap = 0;
+    g.outer0 = 0;
     return g;
 }
 
@@ -79,7 +81,8 @@ __global__ void __launch_bounds__(TK*(N / E))
     // for different output fields (curl prologue) run at the same time and share it through L2
     const int field = blockIdx.x % g.nf;
     const int col = (blockIdx.x / g.nf) * TK + c;
-    const int outer = (int)blockIdx.y < g.outer_lo ? (int)blockIdx.y : (int)blockIdx.y + g.outer_gap;
+    const int oidx = (int)blockIdx.y + g.outer0;
+    const int outer = oidx < g.outer_lo ? oidx : oidx + g.outer_gap;
     const bool active = col < g.ncols;
     const long long base = (long long)outer * g.os + col;
     cplx x[E];
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 template <int N, int E, int LPB, class Op>
 __global__ void __launch_bounds__(LPB*((N / 2) / E))
     xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
-                       int pitch) {
+                       int pitch, long long line0) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     if (!active) line = nlines - 1;
     cplx* plane = reinterpret_cast<cplx*>(b2_smem) + (size_t)ls * PER_LS;
     cplx* park = plane + PS;
-    const long long loff = line * pitch;
+    const long long loff = (line + line0) * pitch;
     cplx x[E];
 #pragma unroll 1
     for (int f = 0; f < NI; ++f) {
@@ -275,13 +278,13 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 template <int N, int E, int MINB, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
-                          int pitch) {
+                          int pitch, long long line0) {
     extern __shared__ double b2_smem[];
     constexpr int M = N / 2, T = M / E, PS = PlaneSize<M, 1>::value;
     constexpr int NI = Op::NI, NO = Op::NO;
     static_assert(T % 32 == 0 || T == 16, "field-parallel x pass: groups are whole warps or half warps");
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    const long long line = blockIdx.x;
+    const long long line = (long long)blockIdx.x + line0;
     cplx* park = reinterpret_cast<cplx*>(b2_smem);    // [NI][E][T] complex
     cplx* plane = park + (size_t)NI * M + (size_t)g * PS;  // per-group exchange plane
     const long long loff = line * pitch;
@@ -330,7 +333,8 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     extern __shared__ double b2_smem[];
     cplx* a = reinterpret_cast<cplx*>(b2_smem);
     cplx* b = a + (size_t)N * TK;
-    const int outer = (int)blockIdx.y < g.outer_lo ? (int)blockIdx.y : (int)blockIdx.y + g.outer_gap;
+    const int oidx = (int)blockIdx.y + g.outer0;
+    const int outer = oidx < g.outer_lo ? oidx : oidx + g.outer_gap;
     const int field = blockIdx.z;
     const int col0 = blockIdx.x * TK;
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {

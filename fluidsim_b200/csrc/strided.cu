@@ -162,10 +162,14 @@ static Geom geom_for_axis(const b2_plan* p, int axis) {
 }
 
 int b2i_strided_plain(b2_plan* p, int axis, int dir, const cplx* const* in, cplx* const* out, int nf,
-                      double scale, cudaStream_t s, bool pruned) {
+                      double scale, cudaStream_t s, bool pruned, int outer0, int nouter) {
     if (axis == 0 && p->n0 == 1) return 0;
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
     Geom g = pruned ? geom_pruned(p, axis, dir) : geom_for_axis(p, axis);
+    if (nouter >= 0) {  // chunked launch over a range of outer indices (y pass: z planes)
+        g.outer0 = outer0;
+        g.nouter = nouter;
+    }
     const int N = axis == 0 ? p->n0 : p->n1;
     const bool fast = axis == 0 ? p->fast0 : p->fast1;
     const cplx* tw = axis == 0 ? p->tw0 : p->tw1;

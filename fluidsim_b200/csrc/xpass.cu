@@ -4,6 +4,9 @@
 #include "internal.h"
 #include "passes.cuh"
 
+static bool g_xpass_share_sm = false;
+void b2i_xpass_share_sm(bool on) { g_xpass_share_sm = on; }
+
 // per-size configuration: E points (of the N/2 complex FFT) per thread
 template <int N> struct XCfg;
 template <> struct XCfg<2048> { static constexpr int E = 16; };  // M=1024, T=64
@@ -122,27 +125,35 @@ static int launch_r2c_n(const double* X, cplx* K, long long nlines, const cplx* 
 }
 
 template <int N, class Op>
-static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, cudaStream_t s) {
+static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, long long line0,
+                  cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
-    auto kern = getenv("B2_XMINB") ? xpass_fused_fp_kernel<N, E, 2, Op> : xpass_fused_fp_kernel<N, E, 1, Op>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+    // b2i_xpass_share_sm(true): run with <= 80 registers and a shared-memory request padded above
+    // half an SM, so that exactly one x-pass CTA plus one strided-pass CTA are co-resident per SM
+    // (the x pass is L1/FP64 bound, the y passes are HBM bound: they overlap, see api.cu)
+    const bool share = g_xpass_share_sm;
+    auto kern = share ? xpass_fused_fp_kernel<N, E, 2, Op> : xpass_fused_fp_kernel<N, E, 1, Op>;
+    size_t smem_req = smem;
+    if (share && smem_req < 118 * 1024) smem_req = 118 * 1024;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[share]) {
+        if (smem_req > 48 * 1024)
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
+        attr_done[share] = true;
     }
-    kern<<<(unsigned)nlines, Op::NI * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch);
+    kern<<<(unsigned)nlines, Op::NI * T, smem_req, s>>>(op, nlines, tw, scale, nkeep, pitch, line0);
     B2_LAUNCH_CHECK("xpass_fused_fp_kernel");
     return 0;
 }
 
 template <int N, class Op>
-static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, cudaStream_t s) {
+static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch, long long line0,
+                  cudaStream_t s) {
     constexpr int E = XCfg<N>::E, M = N / 2, T = M / E;
     constexpr size_t smem_fp = ((size_t)Op::NI * M + (size_t)Op::NI * PlaneSize<M, 1>::value) * sizeof(cplx);
     if constexpr ((T % 32 == 0 || (T == 16 && (Op::NI * T) % 32 == 0)) && smem_fp <= 227 * 1024)
-        return launch_fused_fp_n<N>(op, nlines, tw, scale, nkeep, pitch, s);
+        return launch_fused_fp_n<N>(op, nlines, tw, scale, nkeep, pitch, line0, s);
     constexpr size_t per_ls = ((size_t)PlaneSize<M, 1>::value + (size_t)Op::NI * M) * sizeof(cplx);
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
@@ -155,7 +166,7 @@ static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale,
         attr_done = true;
     }
     const unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);
-    kern<<<grid, LPB * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch);
+    kern<<<grid, LPB * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch, line0);
     B2_LAUNCH_CHECK("xpass_fused_kernel");
     return 0;
 }
@@ -255,32 +266,34 @@ int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream
 }
 
 template <class Op>
-static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int nkeep, int pitch, cudaStream_t s) {
+static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int nkeep, int pitch, long long line0,
+                  cudaStream_t s) {
     switch (p->n2) {
-#define B2_CASE(n) case n: return launch_fused_n<n>(op, nlines, p->tw2, scale, nkeep, pitch, s);
+#define B2_CASE(n) case n: return launch_fused_n<n>(op, nlines, p->tw2, scale, nkeep, pitch, line0, s);
         B2_XSIZES(B2_CASE)
 #undef B2_CASE
     }
     return b2i_set_error("fused x pass: nx=%d not supported (power of two in [8, 2048])", p->n2);
 }
 
-int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch, cudaStream_t s) {
+int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch, long long line0,
+                  cudaStream_t s) {
     if (!p->fast2) return b2i_set_error("fused x pass needs a power-of-two nx");
     if (p->solver == B2_SOLVER_NS3D) {
         OpNS3D op;
         for (int f = 0; f < 6; ++f) op.in[f] = W[f];
         for (int f = 0; f < 3; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
+        return launch_fused(p, op, nlines, scale, nkeep, pitch, line0, s);
     }
     if (p->solver == B2_SOLVER_NS3D_STRAT) {
         OpStrat op;
         for (int f = 0; f < 7; ++f) op.in[f] = W[f];
         for (int f = 0; f < 6; ++f) op.out[f] = W[f];
-        return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
+        return launch_fused(p, op, nlines, scale, nkeep, pitch, line0, s);
     }
     OpNS2D op;
     for (int f = 0; f < 4; ++f) op.in[f] = W[f];
     op.out[0] = W[0];
     op.beta = p->beta;
-    return launch_fused(p, op, nlines, scale, nkeep, pitch, s);
+    return launch_fused(p, op, nlines, scale, nkeep, pitch, line0, s);
 }

@@ -1,0 +1,10 @@
+#!/bin/bash
+timeout 600 python -m pytest tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -3
+run() { timeout 300 python bench.py --size $1 --steps 4 --warmup 2 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys;d=json.loads([l for l in sys.stdin if l.startswith('{')][-1]);print('$2', $1, 'ms/step', round(d['ms_per_step'],2), 'frac', round(d['step_roofline']['frac'],3), ' '.join(k[:6]+':'+str(round(v['avg_ms'],2)) for k,v in d['kernel_classes'].items()))"; }
+B2_NCHUNK=1 run 1024 nchunk1
+B2_NCHUNK=4 run 1024 nchunk4
+run 1024 nchunk8
+B2_NCHUNK=16 run 1024 nchunk16
+B2_NCHUNK=1 run 512 nchunk1
+run 512 nchunk8
