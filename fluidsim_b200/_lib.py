@@ -72,9 +72,10 @@ SIGNATURES = {
     "b2_slab_set_pruning": [_p, _i, _i, _i, _i, _i, _i, _i, _i],
     "b2_slab_curl": [_p, _p, _p],
     "b2_slab_zinv": [_p, _p, _i, _i, _p],
-    "b2_slab_yinv": [_p, _i, _i, _p],
-    "b2_slab_xpass": [_p, _p],
-    "b2_slab_yfwd": [_p, _i, _i, _p],
+    "b2_slab_set_chunks": [_p, _i],
+    "b2_slab_yinv": [_p, _i, _i, _i, _p],
+    "b2_slab_xpass": [_p, _i, _p],
+    "b2_slab_yfwd": [_p, _i, _i, _i, _p],
     "b2_slab_zfwd": [_p, _i, _i, _p],
     "b2_slab_rk": [_p, _i, _i, _d, _p, _p, _p, _p],
     "b2_slab_phase_a": [_p, _p, _i, _p],

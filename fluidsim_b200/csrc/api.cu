@@ -142,6 +142,7 @@ extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double
     p->fast1 = is_pow2(nz) && nz >= 8 && nz <= 2048;
     p->fast2 = is_pow2(nx) && nx >= 8 && nx <= 2048;
     p->fasty = is_pow2(ny) && ny >= 8 && ny <= 2048;
+    p->slab_nc = 1;
     int e = 0;
     e |= upload_twiddles(1, &p->tw0);
     e |= upload_twiddles(nz, &p->tw1);
@@ -1286,13 +1287,22 @@ extern "C" int b2_slab_zinv(b2_plan* p, const double* S_in, int f0, int f1, void
     return b2i_slab_zpass(p, +1, in, out, f1 - f0, s);
 }
 
-// y-inverse of fields [f0, f1): xb -> (pruned: xa expanded | unpruned: xb in place)
-extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, void* stream) {
+// number of z chunks of the exchange layout (pipelining granularity); nz_loc must be a multiple
+extern "C" int b2_slab_set_chunks(b2_plan* p, int nc) {
+    if (!p->slab) return b2i_set_error("b2_slab_set_chunks: not a slab plan");
+    if (nc < 1 || p->nzl % nc) return b2i_set_error("b2_slab_set_chunks: nz_loc=%d not a multiple of %d", p->nzl, nc);
+    p->slab_nc = nc;
+    return 0;
+}
+
+// y-inverse of fields [f0, f1), z chunk `chunk` (-1: all): xb -> (pruned: xa expanded | unpruned: xb)
+extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, int chunk, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e, nin, nout;
     if ((e = slab_ready(p))) return e;
     slab_counts(p, &nin, &nout);
     if (f0 < 0 || f1 > nin || f0 >= f1) return b2i_set_error("b2_slab_yinv: bad field range");
+    if (chunk >= p->slab_nc) return b2i_set_error("b2_slab_yinv: bad chunk");
     const long long fs = p->fsize();
     const cplx* in[8];
     cplx* out[8];
@@ -1301,30 +1311,36 @@ extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, void* stream) {
         out[f - f0] = p->prune ? p->xa + f * fs : p->xb + f * fs;
     }
     ProfScope ps(PC_Y_INV, s);
-    return b2i_slab_ypass(p, +1, in, out, f1 - f0, s);
+    for (int c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? p->slab_nc : chunk + 1); ++c)
+        if ((e = b2i_slab_ypass(p, +1, in, out, f1 - f0, c, s))) return e;
+    return 0;
 }
 
-extern "C" int b2_slab_xpass(b2_plan* p, void* stream) {
+extern "C" int b2_slab_xpass(b2_plan* p, int chunk, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e, nin, nout;
     if ((e = slab_ready(p))) return e;
     slab_counts(p, &nin, &nout);
+    if (chunk >= p->slab_nc) return b2i_set_error("b2_slab_xpass: bad chunk");
     const long long fs = p->fsize();
     cplx* XW[8];
     for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * fs : p->xb + f * fs;
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
     const int pitch = p->prune ? p->keepx : p->nk;
+    const long long lines_c = (long long)p->gy * (p->nzl / p->slab_nc);
     ProfScope ps(PC_X_FUSED, s);
-    return b2i_xpass_fused(p, XW, (long long)p->gy * p->nzl, scale, pitch, pitch, 0, s);
+    if (chunk < 0) return b2i_xpass_fused(p, XW, lines_c * p->slab_nc, scale, pitch, pitch, 0, s);
+    return b2i_xpass_fused(p, XW, lines_c, scale, pitch, pitch, lines_c * chunk, s);
 }
 
-// y-forward of output fields [f0, f1): (pruned: xa -> xb compact | unpruned: xb in place)
-extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, void* stream) {
+// y-forward of output fields [f0, f1), z chunk `chunk` (-1: all): (pruned: xa -> xb compact | xb)
+extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, int chunk, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e, nin, nout;
     if ((e = slab_ready(p))) return e;
     slab_counts(p, &nin, &nout);
     if (f0 < 0 || f1 > nout || f0 >= f1) return b2i_set_error("b2_slab_yfwd: bad field range");
+    if (chunk >= p->slab_nc) return b2i_set_error("b2_slab_yfwd: bad chunk");
     const long long fs = p->fsize();
     const cplx* in[8];
     cplx* out[8];
@@ -1333,7 +1349,9 @@ extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, void* stream) {
         out[f - f0] = p->xb + f * fs;
     }
     ProfScope ps(PC_Y_FWD, s);
-    return b2i_slab_ypass(p, -1, in, out, f1 - f0, s);
+    for (int c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? p->slab_nc : chunk + 1); ++c)
+        if ((e = b2i_slab_ypass(p, -1, in, out, f1 - f0, c, s))) return e;
+    return 0;
 }
 
 // z-forward of output fields [f0, f1): xa (exchange layout) -> work (K layout)
@@ -1380,9 +1398,9 @@ extern "C" int b2_slab_phase_b(b2_plan* p, void* stream) {
     int e, nin, nout;
     if ((e = slab_ready(p))) return e;
     slab_counts(p, &nin, &nout);
-    if ((e = b2_slab_yinv(p, 0, nin, stream))) return e;
-    if ((e = b2_slab_xpass(p, stream))) return e;
-    return b2_slab_yfwd(p, 0, nout, stream);
+    if ((e = b2_slab_yinv(p, 0, nin, -1, stream))) return e;
+    if ((e = b2_slab_xpass(p, -1, stream))) return e;
+    return b2_slab_yfwd(p, 0, nout, -1, stream);
 }
 extern "C" int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S_,
                                double* T_out, void* stream) {

@@ -38,6 +38,7 @@ struct b2_plan {
     bool streams_ready;
     cplx *xa, *xb; // exchange buffers (b2_slab_set_buffers), nwork fields each
     int gyk_lo, gyk_hi;  // global dealiased ky band (pruned slab y passes)
+    int slab_nc;         // z chunks of the exchange layout (b2_slab_set_chunks)
     long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
     long long xsize() const { return (long long)n0 * n1 * n2; }
 };
@@ -75,4 +76,5 @@ void b2i_xpass_share_sm(bool on);
 //   dir = -1 (forward): in = exchange-layout receive buffers, out = K-layout fields
 int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s);
 // y pass in place on receive buffers viewed as (ny, nz_loc, nk)
-int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s);
+int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, int chunk,
+                   cudaStream_t s);

@@ -240,16 +240,22 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 }
 
 // ------------------------------------------------------------------------------- slab passes
-// Index map between K-layout coordinates (yl = outer, z = i, kx = col) and the exchange layout
-// [peer q = z / nzl][kept local ky row][zl = z % nzl][kx < pitch] of one field.  With pruning only
-// the kept local ky rows (compact index) and the kept kx columns are exchanged.
+// Index map between K-layout coordinates (yl = outer, z = i, kx = col) and the exchange layout of one
+// field: [z chunk c][peer q = z / nzl][kept local ky row][z within chunk][kx < pitch].  The z range of
+// every peer is cut in `nc` chunks so that the host can pipeline the all-to-all of chunk c+1 with
+// the y / x passes of chunk c; chunk regions are `cstride` elements apart (sized for the expanded
+// (ny, zc, pitch) array the y-inverse pass writes over the same region).  With pruning only the kept
+// local ky rows (compact index) and the kept kx columns are exchanged.
 struct SlabMapper {
-    int nzl, nkl, pitch, y_lo, y_gap;
+    int nzl, nkl, pitch, y_lo, y_gap, zc;
+    long long cstride;
     B2_DEVINL long long operator()(int z, int kx, int yl) const {
         const int q = z / nzl;
         const int zl = z - q * nzl;
+        const int c = zl / zc;
+        const int zlc = zl - c * zc;
         const int ylc = yl < y_lo ? yl : yl - y_gap;
-        return (((long long)q * nkl + ylc) * nzl + zl) * pitch + kx;
+        return c * cstride + (((long long)q * nkl + ylc) * zc + zlc) * pitch + kx;
     }
 };
 struct SlabStore {
@@ -276,6 +282,7 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     g.nf = nf;
     SlabMapper map;
     map.nzl = p->nzl;
+    map.zc = p->nzl / p->slab_nc;
     if (p->prune) {
         g.ncols = p->keepx;
         g.nouter = p->keep0_lo + (p->n0 - p->keep0_hi);  // kept local ky rows
@@ -291,6 +298,7 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
         g.nouter = p->n0;
         map.nkl = p->n0; map.pitch = p->nk; map.y_lo = 1 << 30; map.y_gap = 0;
     }
+    map.cstride = (long long)p->gy * map.zc * map.pitch;
     if (g.nouter == 0) return 0;  // this rank owns only dealiased ky rows
     if (dir > 0) {
         PlainIn ld;
@@ -306,26 +314,33 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     return launch_strided<-1>(p->fast1, p->n1, g, nf, ld, st, p->tw1, s);
 }
 
-// y pass on the z-slab side.  Unpruned: in place on (ny, nz_loc, nk).  Pruned: the exchanged array
-// holds only the kept ky rows (compact) and kx < keepx columns; the inverse pass expands it to all
-// ny rows (in -> out), the forward pass stores the kept rows back in compact form.
-int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, cudaStream_t s) {
+// y pass on the z-slab side, z chunk `chunk` (sub-array of zc = nz_loc / nc planes).  Unpruned: in
+// place on (ny, zc, nk).  Pruned: the exchanged array holds only the kept ky rows (compact) and
+// kx < keepx columns; the inverse pass expands it to all ny rows (in -> out), the forward pass
+// stores the kept rows back in compact form.  `in` / `out` are the field bases; the chunk offsets
+// (compact: nyk rows, expanded: ny rows) are applied here.
+int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, int chunk,
+                   cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
     Geom g = geom_init();
     const int pitch = p->prune ? p->keepx : p->nk;
-    g.ncols = p->nzl * pitch;
-    g.es = (long long)p->nzl * pitch;
+    const int zc = p->nzl / p->slab_nc;
+    const int nyk = p->prune ? p->gy - (p->gyk_hi - p->gyk_lo) : p->gy;
+    const long long cs_full = (long long)p->gy * zc * pitch, cs_compact = (long long)nyk * zc * pitch;
+    g.ncols = zc * pitch;
+    g.es = (long long)zc * pitch;
     g.nf = nf;
     g.wide = 1;
+    long long in_off = chunk * cs_full, out_off = chunk * cs_full;
     if (p->prune) {
         g.band_lo = p->gyk_lo;
         g.band_hi = p->gyk_hi;
-        if (dir > 0) { g.skip_load = 1; g.ld_lo = p->gyk_lo; g.ld_gap = p->gyk_hi - p->gyk_lo; }
-        else { g.skip_store = 1; g.st_lo = p->gyk_lo; g.st_gap = p->gyk_hi - p->gyk_lo; }
+        if (dir > 0) { g.skip_load = 1; g.ld_lo = p->gyk_lo; g.ld_gap = p->gyk_hi - p->gyk_lo; in_off = chunk * cs_compact; }
+        else { g.skip_store = 1; g.st_lo = p->gyk_lo; g.st_gap = p->gyk_hi - p->gyk_lo; out_off = chunk * cs_compact; }
     }
     PlainIn ld;
     PlainStore st;
-    for (int f = 0; f < nf; ++f) { ld.in[f] = in[f]; st.out[f] = out[f]; }
+    for (int f = 0; f < nf; ++f) { ld.in[f] = in[f] + in_off; st.out[f] = out[f] + out_off; }
     return dir < 0 ? launch_strided<-1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s)
                    : launch_strided<+1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s);
 }

@@ -39,12 +39,18 @@ def global_from_local(parts):
     return np.ascontiguousarray(np.concatenate([np.swapaxes(p, -3, -2) for p in parts], axis=-2))
 
 
-def exchange_index(z, kx, yl, nzl, nyl, nk):
-    """Offset of K-layout element (yl, z, kx) in the exchange layout [peer][ky_loc][z_loc][kx]
-    (restated by ``SlabMapper`` in csrc/strided.cu)."""
+def exchange_index(z, kx, yl, nzl, nyl, nk, nchunks=1, ny=None):
+    """Offset of K-layout element (yl, z, kx) in the exchange layout
+    [z chunk][peer][ky_loc][z in chunk][kx] (restated by ``SlabMapper`` in csrc/strided.cu; unpruned
+    case: every local ky row and kx column is exchanged).  Chunk regions are ``ny * zc * nk``
+    elements apart."""
     r = z // nzl
     zl = z - r * nzl
-    return ((r * nyl + yl) * nzl + zl) * nk + kx
+    zc = nzl // nchunks
+    c = zl // zc
+    zlc = zl - c * zc
+    cstride = 0 if nchunks == 1 else ny * zc * nk
+    return c * cstride + ((r * nyl + yl) * zc + zlc) * nk + kx
 
 
 def check_divisible(nz, ny, world):
@@ -104,7 +110,14 @@ class SlabSimul:
         self._scalar = torch.zeros(1, dtype=torch.float64, device=self.device)
         # dealias-pruned exchange (set up by set_mask...; used once the state is known dealiased)
         self.use_pruning = True
-        self.pipelined = True  # overlap the per-field all-to-alls with the FFT passes
+        self.pipelined = True  # overlap the per-(field, chunk) all-to-alls with the FFT passes
+        # z chunks of the exchange layout (pipelining granularity)
+        import os
+
+        want = int(os.environ.get("B2_SLAB_NCHUNK", "2"))
+        while want > 1 and (self.nzl % want or self.nzl // want < 8):
+            want //= 2
+        self.nchunks = max(1, want)
         self._state_dealiased = False
         self._prune = None
         self._push()
@@ -179,16 +192,7 @@ class SlabSimul:
             lo = min(max(gy_lo - a_r, 0), self.nyl)
             hi = min(max(gy_hi - a_r, 0), self.nyl)
             nkl.append(self.nyl - max(hi - lo, 0))
-        blk = self.nzl * keepx * 2  # float64 elements per kept ky row
-        self._prune = dict(
-            args=(keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi),
-            nkl=nkl,
-            # inverse exchange (K side -> z-slab side): equal blocks out, per-peer row counts in
-            inv_in=[nkl[self.rank] * blk] * self.world,
-            inv_out=[n * blk for n in nkl],
-            fwd_in=[n * blk for n in nkl],
-            fwd_out=[nkl[self.rank] * blk] * self.world,
-        )
+        self._prune = dict(args=(keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi), nkl=nkl)
 
     def gather_state(self):
         """Global sequential-layout state on every rank (testing / small grids only)."""
@@ -197,30 +201,34 @@ class SlabSimul:
         return global_from_local([p.cpu().numpy() for p in parts])
 
     # ---- collectives ------------------------------------------------------------------------------
-    def _all_to_all(self, src, dst, nf, splits=None):
-        """Per field: one contiguous block per peer (NCCL over NVLink; gloo on CPU tests).  Unpruned:
-        ``world`` equal blocks covering the whole field; pruned: only the kept ky rows x kx columns,
-        ``splits = (input_split_sizes, output_split_sizes)`` in float64 elements."""
-        tr = self.torch
-        for f in range(nf):
-            d, s_ = tr.view_as_real(dst[f]).view(-1), tr.view_as_real(src[f]).view(-1)
-            if splits is None:
-                self.dist.all_to_all_single(d, s_, group=self.group)
-            else:
-                ins, outs = splits
-                self.dist.all_to_all_single(d[: sum(outs)], s_[: sum(ins)], outs, ins, group=self.group)
+    def _exchange_plan(self, pr):
+        """Split sizes / chunk strides (in float64 elements) of the per-(field, chunk) all-to-alls."""
+        P, zc = self.world, self.nzl // self.nchunks
+        if pr is None:
+            pitch, nkl = self.nk, [self.nyl] * P
+        else:
+            pitch, nkl = pr["args"][0], pr["nkl"]
+        row = zc * pitch * 2
+        mine = [nkl[self.rank] * row] * P      # K side: equal blocks, one per peer (its z range)
+        theirs = [n * row for n in nkl]        # z-slab side: peer r contributes its kept ky rows
+        return dict(cs_a=self.ny * row, cs_b=sum(nkl) * row, mine=mine, theirs=theirs)
 
-    def _all_to_all_async(self, src, dst, splits):
+    def _a2a(self, src, dst, src_off, dst_off, ins, outs, async_op):
+        """One all-to-all: contiguous per-peer blocks (NCCL over NVLink; gloo on CPU tests)."""
         tr = self.torch
         d, s_ = tr.view_as_real(dst).view(-1), tr.view_as_real(src).view(-1)
-        if splits is None:
-            return self.dist.all_to_all_single(d, s_, group=self.group, async_op=True)
-        ins, outs = splits
-        return self.dist.all_to_all_single(d[: sum(outs)], s_[: sum(ins)], outs, ins, group=self.group,
-                                           async_op=True)
+        return self.dist.all_to_all_single(d[dst_off: dst_off + sum(outs)], s_[src_off: src_off + sum(ins)],
+                                           outs, ins, group=self.group, async_op=async_op)
 
     # ---- stepping ---------------------------------------------------------------------------------
     def _run_stage(self, Sin, need_curl, scheme_id, stage, tout=None, prune=False):
+        """One evaluation of the nonlinear term + RK epilogue.
+
+        K side (z passes, epilogue) and z-slab side (y passes, fused x pass) are separated by two
+        global transposes.  Pipelining: the exchange layout is cut in z chunks; the inverse
+        all-to-all of (field f, chunk c) is issued right after the z-inverse of field f, the y / x
+        passes of chunk c run while chunk c+1 is still in flight, and the forward all-to-all of
+        chunk c overlaps the passes of chunk c+1 (NCCL stream vs. compute stream)."""
         from ._lib import call, ptr, stream_ptr
 
         h = self.handle
@@ -229,40 +237,40 @@ class SlabSimul:
             call("b2_slab_set_pruning", h, 0, 0, 0, 0, 0, 0, 0, 0)
         else:
             call("b2_slab_set_pruning", h, 1, *pr["args"])
-        inv = None if pr is None else (pr["inv_in"], pr["inv_out"])
-        fwd = None if pr is None else (pr["fwd_in"], pr["fwd_out"])
-        if not self.pipelined:
-            call("b2_slab_phase_a", h, ptr(Sin), 1 if need_curl else 0, stream_ptr())
-            self._all_to_all(self._xa, self._xb, self.nwork, inv)
-            call("b2_slab_phase_b", h, stream_ptr())
-            self._all_to_all(self._xb, self._xa, self.nout, fwd)
-            call("b2_slab_phase_c", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect),
-                 ptr(tout), stream_ptr())
-            return
-        # pipelined: the all-to-all of field f runs on NCCL's stream while the FFT passes of the
-        # neighbouring fields run on the compute stream
+        nc = self.nchunks
+        call("b2_slab_set_chunks", h, nc)
+        ex = self._exchange_plan(pr)
         sp = stream_ptr()
+        xa, xb = self._xa, self._xb
+        asyn = self.pipelined
         order = list(range(self.nwork))
         if need_curl:  # v (and b) first: they do not depend on the curl kernel
             order = [0, 1, 2] + list(range(6, self.nwork)) + [3, 4, 5]
-        works = {}
+        inv = {}
         curl_done = not need_curl
         for f in order:
             if not curl_done and 3 <= f < 6:
                 call("b2_slab_curl", h, ptr(Sin), sp)
                 curl_done = True
             call("b2_slab_zinv", h, ptr(Sin), f, f + 1, sp)
-            works[f] = self._all_to_all_async(self._xa[f], self._xb[f], inv)
-        for f in order:
-            works[f].wait()
-            call("b2_slab_yinv", h, f, f + 1, sp)
-        call("b2_slab_xpass", h, sp)
-        works = {}
+            inv[(f, 0)] = self._a2a(xa[f], xb[f], 0, 0, ex["mine"], ex["theirs"], asyn)
+        for c in range(1, nc):
+            for f in order:
+                inv[(f, c)] = self._a2a(xa[f], xb[f], c * ex["cs_a"], c * ex["cs_b"], ex["mine"], ex["theirs"], asyn)
+        fwd = {}
+        for c in range(nc):
+            for f in order:
+                if asyn:
+                    inv[(f, c)].wait()
+                call("b2_slab_yinv", h, f, f + 1, c, sp)
+            call("b2_slab_xpass", h, c, sp)
+            for f in range(self.nout):
+                call("b2_slab_yfwd", h, f, f + 1, c, sp)
+                fwd[(f, c)] = self._a2a(xb[f], xa[f], c * ex["cs_b"], c * ex["cs_a"], ex["theirs"], ex["mine"], asyn)
         for f in range(self.nout):
-            call("b2_slab_yfwd", h, f, f + 1, sp)
-            works[f] = self._all_to_all_async(self._xb[f], self._xa[f], fwd)
-        for f in range(self.nout):
-            works[f].wait()
+            if asyn:
+                for c in range(nc):
+                    fwd[(f, c)].wait()
             call("b2_slab_zfwd", h, f, f + 1, sp)
         call("b2_slab_rk", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout), sp)
 

@@ -156,9 +156,12 @@ int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int
  * all-to-alls with the FFT passes of the other fields (fluidsim_b200/slab.py) */
 int b2_slab_curl(b2_plan* p, const double* S_in, void* stream);
 int b2_slab_zinv(b2_plan* p, const double* S_in, int f0, int f1, void* stream);
-int b2_slab_yinv(b2_plan* p, int f0, int f1, void* stream);
-int b2_slab_xpass(b2_plan* p, void* stream);
-int b2_slab_yfwd(b2_plan* p, int f0, int f1, void* stream);
+/* the exchange layout is cut in nc z chunks ([chunk][peer][ky_loc][z in chunk][kx]) so that the
+ * all-to-all of chunk c+1 overlaps the y / x passes of chunk c; chunk = -1 means all chunks */
+int b2_slab_set_chunks(b2_plan* p, int nc);
+int b2_slab_yinv(b2_plan* p, int f0, int f1, int chunk, void* stream);
+int b2_slab_xpass(b2_plan* p, int chunk, void* stream);
+int b2_slab_yfwd(b2_plan* p, int f0, int f1, int chunk, void* stream);
 int b2_slab_zfwd(b2_plan* p, int f0, int f1, void* stream);
 int b2_slab_rk(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S, double* T_out,
                void* stream);

@@ -13,23 +13,28 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _model_inverse_fft(k_loc, rank, world, nz, ny, nx):
+def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1):
     """Distributed unnormalised inverse FFT of one field following the GPU phases' layouts."""
     from fluidsim_b200.slab import exchange_index
 
     nyl, nzl, nk = ny // world, nz // world, nx // 2 + 1
+    zc = nzl // nchunks
     # phase A: z-inverse on (ny_loc, nz, nk), stored in the exchange layout
     a = np.fft.ifft(k_loc, axis=1) * nz
     send = np.empty(nyl * nz * nk, dtype=np.complex128)
     yl, z, kx = np.meshgrid(np.arange(nyl), np.arange(nz), np.arange(nk), indexing="ij")
-    send[exchange_index(z, kx, yl, nzl, nyl, nk)] = a
+    send[exchange_index(z, kx, yl, nzl, nyl, nk, nchunks, ny)] = a
     recv = np.empty_like(send)
-    dist.all_to_all_single(torch.view_as_real(torch.from_numpy(recv)).view(-1),
-                           torch.view_as_real(torch.from_numpy(send)).view(-1))
-    # phase B: the received buffer IS (ny, nz_loc, nk); y-inverse then c2r along x
-    b = recv.reshape(ny, nzl, nk)
-    b = np.fft.ifft(b, axis=0) * ny
-    return np.fft.irfft(b, n=nx, axis=2) * nx  # (ny, nz_loc, nx)
+    cs = ny * zc * nk  # chunk stride (complex elements): one all-to-all per chunk
+    out = np.empty((ny, nzl, nx))
+    for c in range(nchunks):
+        dist.all_to_all_single(torch.view_as_real(torch.from_numpy(recv[c * cs:(c + 1) * cs])).view(-1),
+                               torch.view_as_real(torch.from_numpy(send[c * cs:(c + 1) * cs])).view(-1))
+        # phase B: the received chunk IS (ny, zc, nk); y-inverse then c2r along x
+        b = recv[c * cs:(c + 1) * cs].reshape(ny, zc, nk)
+        b = np.fft.ifft(b, axis=0) * ny
+        out[:, c * zc:(c + 1) * zc] = np.fft.irfft(b, n=nx, axis=2) * nx
+    return out  # (ny, nz_loc, nx)
 
 
 def _worker(rank, world, port, q):
@@ -50,10 +55,12 @@ def _worker(rank, world, port, q):
         dist.all_gather_object(parts, k_loc)
         assert np.array_equal(global_from_local(parts), kg)
         # distributed inverse transform == this rank's z-slab of the sequential inverse
-        got = _model_inverse_fft(k_loc, rank, world, nz, ny, nx)
         nzl = nz // world
         ref = np.swapaxes(x[rank * nzl:(rank + 1) * nzl], 0, 1)  # (ny, nz_loc, nx)
-        err = np.abs(got - ref).max()
+        err = 0.0
+        for nchunks in (1, 2):
+            got = _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks)
+            err = max(err, np.abs(got - ref).max())
         q.put((rank, float(err)))
     finally:
         dist.destroy_process_group()

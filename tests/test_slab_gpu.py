@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, nchunks, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
@@ -39,6 +39,8 @@ def _worker(rank, world, port, name, q):
         for key in list(kw):
             setattr(p, key, kw.pop(key))
         sim = SlabSimul(solver, p)
+        if nchunks and sim.nzl % nchunks == 0:
+            sim.nchunks = nchunks
         sim.set_mask_from_global(z["mask"])
         sim.set_state_from_global(z["state0"])
         tend = sim.tendencies_nonlin()
@@ -60,8 +62,8 @@ def _worker(rank, world, port, name, q):
 
 
 @pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "strat_16x8x32_rk2"])
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_slab_matches_reference_golden(name, world):
+@pytest.mark.parametrize("world,nchunks", [(2, 1), (2, 2), (4, 2), (8, 1), (8, 2)])
+def test_slab_matches_reference_golden(name, world, nchunks):
     import torch
     import torch.multiprocessing as mp
 
@@ -73,8 +75,8 @@ def test_slab_matches_reference_golden(name, world):
         pytest.skip("grid not divisible")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() + world * 7 + len(name)) % 300
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    port = 29600 + (os.getpid() + world * 7 + nchunks * 3 + len(name)) % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, nchunks, q)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
