@@ -303,3 +303,54 @@ def test_pruned_128_taylor_green_and_noise():
         o, sim, worst = _run_both(meta, 6, init)
         assert sim._state_dealiased
         assert worst < 1e-10
+
+
+# ------------------------------------------------------------------ BASELINE sizes: properties
+def test_512_properties_fft_roundtrip_energy_and_pruning():
+    """At 512^3 (BASELINE config 3 size) the oracle is too slow; check size-independent properties:
+    FFT round trip, Parseval (phys/spect energy), energy conservation of the nonlinear term,
+    divergence-free dealiased state after steps, pruned == unpruned."""
+    torch = _torch()
+    meta = dict(solver="ns3d", shape=(512, 512, 512), params=dict(nu_8=1e-20, deltat0=1e-3))
+    sim = make_gpu_sim(meta, fused=True)
+    oper = sim.oper
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(oper.shapeX_loc, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    k = oper.fft(x)
+    assert float((oper.ifft(k) - x).abs().max()) < 5e-15
+    # Parseval with the r2c-aware sum (sum_wavenumbers semantics)
+    e_x = oper.compute_energy_from_X(x)
+    e_k = oper.compute_energy_from_K(k)
+    assert abs(e_x - e_k) < 1e-13 * e_x
+    v = [k]
+    for _ in range(2):
+        x.uniform_(-0.5, 0.5, generator=g)
+        v.append(oper.fft(x))
+    del x
+    oper.project_perpk3d(*v)
+    oper.dealiasing(*v)
+    sim.state.init_statespect_from(vx_fft=v[0], vy_fft=v[1], vz_fft=v[2])
+    del v, k
+    T = sim.tendencies_nonlin_fused().tensor
+    S = sim.state.state_spect.tensor
+    tot = tot_abs = 0.0
+    for i in range(3):
+        r = (T[i].conj() * S[i]).real
+        tot += oper.sum_wavenumbers(r)
+        tot_abs += oper.sum_wavenumbers(r.abs())
+        del r
+    assert abs(tot) / tot_abs < 1e-12
+    del T
+    s0 = S.clone()
+    for _ in range(2):  # step 1 unpruned, step 2 pruned
+        sim.time_stepping.one_time_step()
+    a = S.clone()
+    sim.use_pruning = False
+    sim.state.state_spect.tensor.copy_(s0)
+    sim.state.mark_spect_modified()
+    del s0
+    for _ in range(2):
+        sim.time_stepping.one_time_step()
+    assert float((a - S).abs().max()) <= 1e-13 * float(a.abs().max())
+    assert float(oper.divfft_from_vecfft(S[0], S[1], S[2]).abs().max()) < 1e-10
+    assert float(S[0][oper.where_dealiased.bool()].abs().max()) == 0.0
