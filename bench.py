@@ -278,7 +278,7 @@ def make_slab_sim(args, torch, dist):
     dev = sim.device
     dk = 2 * math.pi / (2 * math.pi)
     kadim = lambda m: torch.fft.fftfreq(m, 1.0 / m, dtype=torch.float64, device=dev).abs()
-    ky = dk * kadim(n)[sim.rank * sim.nyl:(sim.rank + 1) * sim.nyl]
+    ky = dk * (kadim(n)[sim.rank::sim.world] if sim.cyclic else kadim(n)[sim.rank * sim.nyl:(sim.rank + 1) * sim.nyl])
     kz = dk * kadim(n)
     kx = dk * torch.arange(n // 2 + 1, dtype=torch.float64, device=dev)
     c = 2.0 / 3

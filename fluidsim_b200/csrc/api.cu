@@ -57,12 +57,13 @@ static int upload_twiddles(int n, cplx** out) {
     return 0;
 }
 
-static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** out, int first = 0) {
+static int upload_wavenumbers(int n, int nkeep, double L, bool half, double** out, int first = 0,
+                              int stride = 1) {
     // fluidfft k_adim ordering: [0..n/2, -n/2+1..-1] (np.fft.fftfreq*n with +n/2 for even n)
     std::vector<double> h(nkeep > 0 ? nkeep : 1, 0.0);
     const double dk = L > 0 ? 2.0 * M_PI / L : 0.0;
     for (int j = 0; j < nkeep; ++j) {
-        const int i = first + j;
+        const int i = first + j * stride;
         int k = i;
         if (!half && i > n / 2) k = i - n;
         h[j] = dk * (double)k;
@@ -117,10 +118,29 @@ extern "C" int b2_plan_create(b2_plan** out, int ndim, int n0, int n1, int n2, d
 // local K layout (ny_loc, nz, nx/2+1), dimX_K = (1, 0, 2) -- the layout of fluidfft's
 // fft3d.mpi_with_fftwmpi3d that fluidsim already handles
 // (/root/reference/fluidsim/operators/operators3d.py:384-391).
+void b2i_slab_local_band(const b2_plan* p, int r, int* lo, int* hi) {
+    const int nyl = p->nyl, P = p->nranks;
+    const int glo = p->prune ? p->gyk_lo : p->gy, ghi = p->prune ? p->gyk_hi : p->gy;
+    auto clampi = [&](long long v) { return (int)(v < 0 ? 0 : (v > nyl ? nyl : v)); };
+    int l, h;
+    if (p->ky_cyclic) {  // global row = yl * P + r
+        auto ceil_div = [&](long long a) { return a <= 0 ? 0 : (a + P - 1) / P; };
+        l = clampi(ceil_div((long long)glo - r));
+        h = clampi(ceil_div((long long)ghi - r));
+    } else {  // global row = r * nyl + yl
+        l = clampi((long long)glo - (long long)r * nyl);
+        h = clampi((long long)ghi - (long long)r * nyl);
+    }
+    if (h <= l) l = h = nyl;
+    *lo = l;
+    *hi = h;
+}
+
 extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx,
-                                   int rank, int nranks) {
+                                   int rank, int nranks, int ky_cyclic) {
     if (!out) return b2i_set_error("b2_plan_create_slab: out is NULL");
     if (nranks < 1 || rank < 0 || rank >= nranks) return b2i_set_error("b2_plan_create_slab: bad rank");
+    if (nranks > 8) return b2i_set_error("b2_plan_create_slab: at most 8 ranks (one node)");
     if (nz % nranks || ny % nranks)
         return b2i_set_error("b2_plan_create_slab: nz=%d and ny=%d must be multiples of nranks=%d", nz, ny,
                              nranks);
@@ -143,12 +163,14 @@ extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double
     p->fast2 = is_pow2(nx) && nx >= 8 && nx <= 2048;
     p->fasty = is_pow2(ny) && ny >= 8 && ny <= 2048;
     p->slab_nc = 1;
+    p->ky_cyclic = ky_cyclic ? 1 : 0;
     int e = 0;
     e |= upload_twiddles(1, &p->tw0);
     e |= upload_twiddles(nz, &p->tw1);
     e |= upload_twiddles(nx, &p->tw2);
     e |= upload_twiddles(ny, &p->twy);
-    e |= upload_wavenumbers(ny, p->nyl, Ly, false, &p->k0, rank * p->nyl);
+    if (ky_cyclic) e |= upload_wavenumbers(ny, p->nyl, Ly, false, &p->k0, rank, nranks);
+    else e |= upload_wavenumbers(ny, p->nyl, Ly, false, &p->k0, rank * p->nyl);
     e |= upload_wavenumbers(nz, nz, Lz, false, &p->k1);
     e |= upload_wavenumbers(nx, p->nk, Lx, true, &p->kx);
     if (e) {
@@ -836,9 +858,26 @@ extern "C" int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int
         return b2i_set_error("b2_slab_set_pruning: inconsistent ranges");
     p->keepx = keepx;
     p->keep1_lo = kz_lo; p->keep1_hi = kz_hi;
-    p->keep0_lo = yl_lo; p->keep0_hi = yl_hi;
     p->gyk_lo = gy_lo; p->gyk_hi = gy_hi;
     p->prune = 1;
+    // the local band follows from the global one and the ky distribution (yl_lo / yl_hi are only
+    // cross-checked so that host and library agree on the layout)
+    b2i_slab_local_band(p, p->rank, &p->keep0_lo, &p->keep0_hi);
+    if (p->keep0_lo != yl_lo || p->keep0_hi != yl_hi) {
+        p->prune = 0;
+        return b2i_set_error("b2_slab_set_pruning: local band [%d, %d) disagrees with the library's [%d, %d)",
+                             yl_lo, yl_hi, p->keep0_lo, p->keep0_hi);
+    }
+    return 0;
+}
+// kept local ky rows of every rank for the current pruning state (all-to-all split sizes)
+extern "C" int b2_slab_kept_rows(const b2_plan* p, int* nkl) {
+    if (!p->slab) return b2i_set_error("b2_slab_kept_rows: not a slab plan");
+    for (int r = 0; r < p->nranks; ++r) {
+        int lo, hi;
+        b2i_slab_local_band(p, r, &lo, &hi);
+        nkl[r] = p->nyl - (hi - lo);
+    }
     return 0;
 }
 /* kept index ranges: out[0..4] = keep0_lo, keep0_hi, keep1_lo, keep1_hi, keepx */

@@ -39,6 +39,7 @@ struct b2_plan {
     cplx *xa, *xb; // exchange buffers (b2_slab_set_buffers), nwork fields each
     int gyk_lo, gyk_hi;  // global dealiased ky band (pruned slab y passes)
     int slab_nc;         // z chunks of the exchange layout (b2_slab_set_chunks)
+    int ky_cyclic;       // ky rows dealt round-robin to the ranks (balances the pruned K side)
     long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
     long long xsize() const { return (long long)n0 * n1 * n2; }
 };
@@ -69,6 +70,8 @@ int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream
 int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch,
                     long long line0, cudaStream_t s);
 void b2i_xpass_share_sm(bool on);
+// dealiased band [lo, hi) of the LOCAL ky rows of rank r (lo == hi: none), from the global band
+void b2i_slab_local_band(const b2_plan* p, int r, int* lo, int* hi);
 
 // --- slab (multi-GPU) passes (strided.cu).  Exchange layout of one field: [peer r][ky_loc][z_loc][kx]
 // z pass between the local K layout (ny_loc, nz, nk) and the exchange layout:

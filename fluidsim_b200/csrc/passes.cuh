@@ -14,6 +14,27 @@
 #pragma once
 #include "fft_core.cuh"
 
+#define B2_MAXR 8  // ranks of a slab decomposition (one node)
+
+// Row map of the slab y passes: logical ky row i -> memory row of the exchanged array, whose rows
+// are grouped by owning rank (block or cyclic ky distribution) and hold only the kept rows of each
+// rank (the local dealiased band [lo, lo + gap) is not stored).
+struct RowMap {
+    int P;  // 0: identity
+    int nyl, cyclic;
+    int shift;  // log2 of the divisor (P if cyclic, nyl otherwise) when it is a power of two, else -1
+    int rowstart[B2_MAXR], lo[B2_MAXR], gap[B2_MAXR];
+    B2_DEVINL int operator()(int i) const {
+        if (P == 0) return i;
+        const int d = cyclic ? P : nyl;
+        const int q = shift >= 0 ? (i >> shift) : i / d;
+        const int m = i - q * d;
+        const int r = cyclic ? m : q;
+        const int yl = cyclic ? q : m;
+        return rowstart[r] + (yl < lo[r] ? yl : yl - gap[r]);
+    }
+};
+
 struct Geom {
     int ncols;      // number of columns (contiguous index)
     int nouter;     // number of outer batches
@@ -30,9 +51,10 @@ struct Geom {
     int band_lo, band_hi;
     int skip_load, skip_store;
     int wide;       // prefer the wide-tile configuration (plane-strided lines)
-    // compact row storage: row i of the line lives at memory row (i < lo ? i : i - gap) of the
-    // source (ld_*) / destination (st_*) array (band rows are never touched)
-    int ld_lo, ld_gap, st_lo, st_gap;
+    // row storage of the source (map_load) / destination (map_store) array: rows.operator()(i)
+    // (band rows are never touched)
+    RowMap rows;
+    int map_load, map_store;
     int outer0;     // first outer index of this launch (chunked launches)
 };
 static inline Geom geom_init() {
@@ -40,13 +62,13 @@ static inline Geom geom_init() {
     g.ncols = 0; g.nouter = 1; g.es = 0; g.os = 0; g.cs = 1; g.nf = 1;
     g.outer_lo = 1 << 30; g.outer_gap = 0; g.band_lo = 0; g.band_hi = 0; g.skip_load = 0; g.skip_store = 0;
     g.wide = 0;
-    g.ld_lo = 1 << 30; g.ld_gap = 0; g.st_lo = 1 << 30; g.st_gap = 0;
+    g.rows.P = 0; g.rows.nyl = 1; g.rows.cyclic = 0; g.rows.shift = -1; g.map_load = 0; g.map_store = 0;
+    for (int r = 0; r < B2_MAXR; ++r) { g.rows.rowstart[r] = 0; g.rows.lo[r] = 0; g.rows.gap[r] = 0; }
     g.outer0 = 0;
     return g;
 }
 
 #define B2_MAXF 8
-
 // ------------------------------------------------------------------------------- load/store ops
 struct PlainLoad {
     const cplx* in[B2_MAXF];
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(TK*(N / E))
     for (int m = 0; m < E; ++m) {
         const int i = t + m * T;
         const bool zero = !active || (g.skip_load && i >= g.band_lo && i < g.band_hi);
-        const int il = i < g.ld_lo ? i : i - g.ld_gap;
+        const int il = (g.map_load && !zero) ? g.rows(i) : i;
         x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)il * g.es, i, col, outer);
     }
     fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
@@ -98,9 +120,10 @@ __global__ void __launch_bounds__(TK*(N / E))
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int i = t + m * T;
-            const int is = i < g.st_lo ? i : i - g.st_gap;
-            if (!(g.skip_store && i >= g.band_lo && i < g.band_hi))
+            if (!(g.skip_store && i >= g.band_lo && i < g.band_hi)) {
+                const int is = g.map_store ? g.rows(i) : i;
                 st(field, base + (long long)is * g.es, i, col, outer, x[m]);
+            }
         }
     }
 }
@@ -340,8 +363,9 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
         cplx v = make_double2(0.0, 0.0);
-        const int il = i < g.ld_lo ? i : i - g.ld_gap;
-        if (col < g.ncols && !(g.skip_load && i >= g.band_lo && i < g.band_hi))
+        const bool inband_l = g.skip_load && i >= g.band_lo && i < g.band_hi;
+        const int il = (g.map_load && !inband_l) ? g.rows(i) : i;
+        if (col < g.ncols && !inband_l)
             v = ld(field, (long long)outer * g.os + (long long)il * g.es + (long long)col * g.cs, i, col, outer);
         a[idx] = v;
     }
@@ -376,8 +400,9 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     }
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
-        const int is = i < g.st_lo ? i : i - g.st_gap;
-        if (col < g.ncols && !(g.skip_store && i >= g.band_lo && i < g.band_hi))
+        const bool inband_s = g.skip_store && i >= g.band_lo && i < g.band_hi;
+        const int is = (g.map_store && !inband_s) ? g.rows(i) : i;
+        if (col < g.ncols && !inband_s)
             st(field, (long long)outer * g.os + (long long)is * g.es + (long long)col * g.cs, i, col, outer,
                a[idx]);
     }

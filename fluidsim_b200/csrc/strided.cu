@@ -332,11 +332,38 @@ int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     g.nf = nf;
     g.wide = 1;
     long long in_off = chunk * cs_full, out_off = chunk * cs_full;
+    if (p->prune || p->ky_cyclic) {
+        // the exchanged array has its rows grouped by owning rank (kept rows only when pruned): the
+        // inverse pass reads it through the row map and writes natural ky order, the forward pass
+        // does the opposite
+        g.rows.P = p->nranks;
+        g.rows.nyl = p->nyl;
+        g.rows.cyclic = p->ky_cyclic;
+        {
+            const int d = p->ky_cyclic ? p->nranks : p->nyl;
+            g.rows.shift = -1;
+            if (d > 0 && (d & (d - 1)) == 0) {
+                int sh = 0;
+                while ((1 << sh) < d) ++sh;
+                g.rows.shift = sh;
+            }
+        }
+        int start = 0;
+        for (int r = 0; r < p->nranks; ++r) {
+            int lo, hi;
+            b2i_slab_local_band(p, r, &lo, &hi);
+            g.rows.rowstart[r] = start;
+            g.rows.lo[r] = lo;
+            g.rows.gap[r] = hi - lo;
+            start += p->nyl - (hi - lo);
+        }
+        if (dir > 0) g.map_load = 1; else g.map_store = 1;
+    }
     if (p->prune) {
         g.band_lo = p->gyk_lo;
         g.band_hi = p->gyk_hi;
-        if (dir > 0) { g.skip_load = 1; g.ld_lo = p->gyk_lo; g.ld_gap = p->gyk_hi - p->gyk_lo; in_off = chunk * cs_compact; }
-        else { g.skip_store = 1; g.st_lo = p->gyk_lo; g.st_gap = p->gyk_hi - p->gyk_lo; out_off = chunk * cs_compact; }
+        if (dir > 0) { g.skip_load = 1; in_off = chunk * cs_compact; }
+        else { g.skip_store = 1; out_off = chunk * cs_compact; }
     }
     PlainIn ld;
     PlainStore st;

@@ -26,17 +26,39 @@ from ._lib import SCHEME_IDS, SOLVER_IDS
 
 
 # ----------------------------------------------------------------------------------- layout algebra
-def local_from_global(arr_global, rank, world):
-    """Global sequential K array ``(..., nz, ny, nk)`` -> this rank's ``(..., ny_loc, nz, nk)``."""
+def local_from_global(arr_global, rank, world, cyclic=False):
+    """Global sequential K array ``(..., nz, ny, nk)`` -> this rank's ``(..., ny_loc, nz, nk)``.
+
+    ``cyclic``: ky rows dealt round-robin (global row = yl * world + rank) instead of in blocks."""
     ny = arr_global.shape[-2]
     nyl = ny // world
-    sl = arr_global[..., :, rank * nyl:(rank + 1) * nyl, :]
+    if cyclic:
+        sl = arr_global[..., :, rank::world, :]
+    else:
+        sl = arr_global[..., :, rank * nyl:(rank + 1) * nyl, :]
     return np.ascontiguousarray(np.swapaxes(sl, -3, -2))
 
 
-def global_from_local(parts):
+def global_from_local(parts, cyclic=False):
     """Inverse of ``local_from_global`` given the list of all ranks' local arrays."""
-    return np.ascontiguousarray(np.concatenate([np.swapaxes(p, -3, -2) for p in parts], axis=-2))
+    sw = [np.swapaxes(p, -3, -2) for p in parts]  # (..., nz, ny_loc, nk)
+    if not cyclic:
+        return np.ascontiguousarray(np.concatenate(sw, axis=-2))
+    world = len(sw)
+    shape = list(sw[0].shape)
+    shape[-2] *= world
+    out = np.empty(shape, dtype=sw[0].dtype)
+    for r, a in enumerate(sw):
+        out[..., :, r::world, :] = a
+    return out
+
+
+def exchanged_row(i, world, nyl, cyclic=False):
+    """Row of the z-slab-side (received) array holding global ky row ``i`` (unpruned): rows are
+    grouped by owning rank (``RowMap`` in csrc/passes.cuh)."""
+    if cyclic:
+        return (i % world) * nyl + i // world
+    return i
 
 
 def exchange_index(z, kx, yl, nzl, nyl, nk, nchunks=1, ny=None):
@@ -66,7 +88,7 @@ class SlabSimul:
     state is ``state_spect`` of shape ``(nvar, ny_loc, nz, nk)``.
     """
 
-    def __init__(self, solver, params, group=None):
+    def __init__(self, solver, params, group=None, ky_distribution="auto"):
         import torch
         import torch.distributed as dist
 
@@ -88,9 +110,21 @@ class SlabSimul:
         self.nyl, self.nzl = self.ny // self.world, self.nz // self.world
         self.nk = self.nx // 2 + 1
         self.device = torch.device("cuda", torch.cuda.current_device())
+        import os
+
+        ky_distribution = os.environ.get("B2_SLAB_KY", ky_distribution)
+        if ky_distribution == "auto":
+            # 2 ranks are balanced with blocks already (the dealiased band is centred); from 4 ranks
+            # on, blocks leave the middle ranks with (almost) no kept rows
+            ky_distribution = "cyclic" if self.world >= 4 else "block"
+        if ky_distribution not in ("cyclic", "block"):
+            raise ValueError("ky_distribution must be 'auto', 'cyclic' or 'block'")
+        # "block" is the fftwmpi3d layout; "cyclic" deals the ky rows round-robin so that the kept
+        # (non dealiased) rows -- hence the K-side work of the pruned transforms -- are balanced
+        self.cyclic = ky_distribution == "cyclic"
         handle = C.c_void_p()
         call("b2_plan_create_slab", C.byref(handle), self.nz, self.ny, self.nx, float(po.Lz), float(po.Ly),
-             float(po.Lx), self.rank, self.world)
+             float(po.Lx), self.rank, self.world, 1 if self.cyclic else 0)
         self.handle = handle
         self.shapeK_loc = (self.nyl, self.nz, self.nk)
         self.nvar = 4 if solver == "ns3d.strat" else 3
@@ -136,7 +170,7 @@ class SlabSimul:
     # ---- data in / out ---------------------------------------------------------------------------
     def set_mask_from_global(self, mask_global):
         """``where_dealiased`` of the sequential operator ``(nz, ny, nk)`` -> local slab."""
-        loc = local_from_global(np.asarray(mask_global, dtype=np.uint8), self.rank, self.world)
+        loc = local_from_global(np.asarray(mask_global, dtype=np.uint8), self.rank, self.world, self.cyclic)
         self.set_local_mask(self.torch.from_numpy(loc).to(self.device))
 
     def set_local_mask(self, mask_local):
@@ -145,7 +179,7 @@ class SlabSimul:
         self._setup_pruning()
 
     def set_state_from_global(self, state_global):
-        loc = local_from_global(np.asarray(state_global), self.rank, self.world)
+        loc = local_from_global(np.asarray(state_global), self.rank, self.world, self.cyclic)
         self.state_spect.copy_(self.torch.from_numpy(loc))
         self._state_dealiased = False
 
@@ -175,39 +209,51 @@ class SlabSimul:
         parts = [tr.empty_like(kyl) for _ in range(self.world)]
         dist.all_gather(parts, kyl, group=self.group)
         kx, kz, kyl = kx.cpu().numpy(), kz.cpu().numpy(), kyl.cpu().numpy()
-        kyg = np.concatenate([p.cpu().numpy() for p in parts])
+        kyg = np.empty(self.ny, dtype=kyl.dtype)
+        for r, part in enumerate(parts):
+            if self.cyclic:
+                kyg[r::self.world] = part.cpu().numpy()
+            else:
+                kyg[r * self.nyl:(r + 1) * self.nyl] = part.cpu().numpy()
         keepx = int(np.nonzero(kx)[0].max()) + 1 if kx.any() else 1
         kz_lo, kz_hi = self._band(kz)
         gy_lo, gy_hi = self._band(kyg)
-        # local band = intersection of the global band with this rank's rows (keeps the layouts of
-        # all ranks consistent with the global compact ky index)
-        a = self.rank * self.nyl
-        yl_lo = min(max(gy_lo - a, 0), self.nyl)
-        yl_hi = min(max(gy_hi - a, 0), self.nyl)
-        if yl_hi <= yl_lo:
-            yl_lo = yl_hi = self.nyl
-        nkl = []
-        for r in range(self.world):
-            a_r = r * self.nyl
-            lo = min(max(gy_lo - a_r, 0), self.nyl)
-            hi = min(max(gy_hi - a_r, 0), self.nyl)
-            nkl.append(self.nyl - max(hi - lo, 0))
-        self._prune = dict(args=(keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi), nkl=nkl)
+        yl_lo, yl_hi = self._local_band(self.rank, gy_lo, gy_hi)
+        self._prune = dict(args=(keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi))
+
+    def _local_band(self, r, gy_lo, gy_hi):
+        """Dealiased band of rank r's local ky rows (mirrors ``b2i_slab_local_band``)."""
+        nyl, P = self.nyl, self.world
+        clamp = lambda v: max(0, min(nyl, v))
+        if self.cyclic:
+            cd = lambda a: 0 if a <= 0 else (a + P - 1) // P
+            lo, hi = clamp(cd(gy_lo - r)), clamp(cd(gy_hi - r))
+        else:
+            lo, hi = clamp(gy_lo - r * nyl), clamp(gy_hi - r * nyl)
+        if hi <= lo:
+            lo = hi = nyl
+        return lo, hi
+
+    def _kept_rows(self):
+        """Kept local ky rows per rank for the pruning state last pushed to the library."""
+        from ._lib import call
+
+        arr = (C.c_int * self.world)()
+        call("b2_slab_kept_rows", self.handle, arr)
+        return list(arr)
 
     def gather_state(self):
         """Global sequential-layout state on every rank (testing / small grids only)."""
         parts = [self.torch.empty_like(self.state_spect) for _ in range(self.world)]
         self.dist.all_gather(parts, self.state_spect, group=self.group)
-        return global_from_local([p.cpu().numpy() for p in parts])
+        return global_from_local([p.cpu().numpy() for p in parts], self.cyclic)
 
     # ---- collectives ------------------------------------------------------------------------------
     def _exchange_plan(self, pr):
         """Split sizes / chunk strides (in float64 elements) of the per-(field, chunk) all-to-alls."""
         P, zc = self.world, self.nzl // self.nchunks
-        if pr is None:
-            pitch, nkl = self.nk, [self.nyl] * P
-        else:
-            pitch, nkl = pr["args"][0], pr["nkl"]
+        pitch = self.nk if pr is None else pr["args"][0]
+        nkl = self._kept_rows()
         row = zc * pitch * 2
         mine = [nkl[self.rank] * row] * P      # K side: equal blocks, one per peer (its z range)
         theirs = [n * row for n in nkl]        # z-slab side: peer r contributes its kept ky rows

@@ -145,13 +145,17 @@ int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
  * The all-to-alls exchange, per field, nranks equal contiguous blocks (xa -> xb after phase A for
  * nvar+3 fields, xb -> xa after phase B for 3 (ns3d) / 6 (strat) fields) and are issued by the host
  * side (torch.distributed / NCCL; fluidsim_b200/slab.py). */
+/* ky_cyclic != 0: ky rows are dealt round-robin (global row = yl * nranks + rank) instead of in
+ * contiguous blocks, which balances the kept rows of the pruned transforms between the ranks */
 int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx, int rank,
-                        int nranks);
+                        int nranks, int ky_cyclic);
 int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb);
 /* pruned exchange (see b2_set_pruning): kept ranges agreed between the ranks by the host side; the
  * all-to-alls then carry only the kept local ky rows x kx < keepx (uneven splits) */
 int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int yl_lo, int yl_hi,
                         int gy_lo, int gy_hi);
+/* kept local ky rows of each rank (nranks ints) for the current pruning state */
+int b2_slab_kept_rows(const b2_plan* p, int* nkl);
 /* fine-grained pieces over work-field ranges [f0, f1) -- lets the host pipeline the per-field
  * all-to-alls with the FFT passes of the other fields (fluidsim_b200/slab.py) */
 int b2_slab_curl(b2_plan* p, const double* S_in, void* stream);

@@ -13,9 +13,9 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1):
+def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1, cyclic=False):
     """Distributed unnormalised inverse FFT of one field following the GPU phases' layouts."""
-    from fluidsim_b200.slab import exchange_index
+    from fluidsim_b200.slab import exchange_index, exchanged_row
 
     nyl, nzl, nk = ny // world, nz // world, nx // 2 + 1
     zc = nzl // nchunks
@@ -32,6 +32,8 @@ def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1):
                                torch.view_as_real(torch.from_numpy(send[c * cs:(c + 1) * cs])).view(-1))
         # phase B: the received chunk IS (ny, zc, nk); y-inverse then c2r along x
         b = recv[c * cs:(c + 1) * cs].reshape(ny, zc, nk)
+        # rows arrive grouped by owning rank: bring them to natural ky order (RowMap on the GPU)
+        b = b[[exchanged_row(i, world, nyl, cyclic) for i in range(ny)]]
         b = np.fft.ifft(b, axis=0) * ny
         out[:, c * zc:(c + 1) * zc] = np.fft.irfft(b, n=nx, axis=2) * nx
     return out  # (ny, nz_loc, nx)
@@ -48,19 +50,20 @@ def _worker(rank, world, port, q):
         rng = np.random.default_rng(0)
         x = rng.random((nz, ny, nx))
         kg = np.fft.rfftn(x) / x.size  # sequential layout (nz, ny, nk)
-        k_loc = local_from_global(kg, rank, world)
-        assert k_loc.shape == (ny // world, nz, nx // 2 + 1)
-        # scatter / gather round trip
-        parts = [None] * world
-        dist.all_gather_object(parts, k_loc)
-        assert np.array_equal(global_from_local(parts), kg)
-        # distributed inverse transform == this rank's z-slab of the sequential inverse
         nzl = nz // world
         ref = np.swapaxes(x[rank * nzl:(rank + 1) * nzl], 0, 1)  # (ny, nz_loc, nx)
         err = 0.0
-        for nchunks in (1, 2):
-            got = _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks)
-            err = max(err, np.abs(got - ref).max())
+        for cyclic in (False, True):
+            k_loc = local_from_global(kg, rank, world, cyclic)
+            assert k_loc.shape == (ny // world, nz, nx // 2 + 1)
+            # scatter / gather round trip
+            parts = [None] * world
+            dist.all_gather_object(parts, k_loc)
+            assert np.array_equal(global_from_local(parts, cyclic), kg)
+            # distributed inverse transform == this rank's z-slab of the sequential inverse
+            for nchunks in (1, 2):
+                got = _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks, cyclic)
+                err = max(err, np.abs(got - ref).max())
         q.put((rank, float(err)))
     finally:
         dist.destroy_process_group()

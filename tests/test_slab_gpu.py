@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, nchunks, q):
+def _worker(rank, world, port, name, nchunks, dist_kind, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
@@ -38,7 +38,7 @@ def _worker(rank, world, port, name, nchunks, q):
         p.time_stepping.deltat0 = kw.pop("deltat0")
         for key in list(kw):
             setattr(p, key, kw.pop(key))
-        sim = SlabSimul(solver, p)
+        sim = SlabSimul(solver, p, ky_distribution=dist_kind)
         if nchunks and sim.nzl % nchunks == 0:
             sim.nchunks = nchunks
         sim.set_mask_from_global(z["mask"])
@@ -48,7 +48,7 @@ def _worker(rank, world, port, name, nchunks, q):
         dist.all_gather(parts, tend)
         from fluidsim_b200.slab import global_from_local
 
-        e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts]), z["tend0"])
+        e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts], sim.cyclic), z["tend0"])
         sim.one_time_step()  # unpruned (state not known to be dealiased)
         assert sim._prune is not None
         e_1 = rel_err(sim.gather_state(), z["state1"])
@@ -62,8 +62,9 @@ def _worker(rank, world, port, name, nchunks, q):
 
 
 @pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "strat_16x8x32_rk2"])
-@pytest.mark.parametrize("world,nchunks", [(2, 1), (2, 2), (4, 2), (8, 1), (8, 2)])
-def test_slab_matches_reference_golden(name, world, nchunks):
+@pytest.mark.parametrize("world,nchunks,dist_kind", [(2, 1, "block"), (2, 2, "cyclic"), (4, 2, "cyclic"),
+                                                     (8, 1, "cyclic"), (8, 2, "block")])
+def test_slab_matches_reference_golden(name, world, nchunks, dist_kind):
     import torch
     import torch.multiprocessing as mp
 
@@ -76,7 +77,7 @@ def test_slab_matches_reference_golden(name, world, nchunks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + (os.getpid() + world * 7 + nchunks * 3 + len(name)) % 300
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, nchunks, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, nchunks, dist_kind, q)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
