@@ -26,6 +26,7 @@ struct RowMap {
     int rowstart[B2_MAXR], lo[B2_MAXR], gap[B2_MAXR];
     B2_DEVINL int operator()(int i) const {
         if (P == 0) return i;
+        if (P == 1) return i < lo[0] ? i : i - gap[0];  // block distribution: one global band
         const int d = cyclic ? P : nyl;
         const int q = shift >= 0 ? (i >> shift) : i / d;
         const int m = i - q * d;

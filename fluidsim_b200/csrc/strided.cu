@@ -336,26 +336,33 @@ int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
         // the exchanged array has its rows grouped by owning rank (kept rows only when pruned): the
         // inverse pass reads it through the row map and writes natural ky order, the forward pass
         // does the opposite
-        g.rows.P = p->nranks;
-        g.rows.nyl = p->nyl;
-        g.rows.cyclic = p->ky_cyclic;
-        {
-            const int d = p->ky_cyclic ? p->nranks : p->nyl;
+        if (!p->ky_cyclic) {
+            // block distribution: ranks own increasing ky ranges, so the rank-grouped compact rows
+            // are simply the global rows with the dealiased band removed
+            g.rows.P = 1;
+            g.rows.nyl = p->gy;
+            g.rows.rowstart[0] = 0;
+            g.rows.lo[0] = p->gyk_lo;
+            g.rows.gap[0] = p->gyk_hi - p->gyk_lo;
+        } else {
+            g.rows.P = p->nranks;
+            g.rows.nyl = p->nyl;
+            g.rows.cyclic = 1;
             g.rows.shift = -1;
-            if (d > 0 && (d & (d - 1)) == 0) {
+            if ((p->nranks & (p->nranks - 1)) == 0) {
                 int sh = 0;
-                while ((1 << sh) < d) ++sh;
+                while ((1 << sh) < p->nranks) ++sh;
                 g.rows.shift = sh;
             }
-        }
-        int start = 0;
-        for (int r = 0; r < p->nranks; ++r) {
-            int lo, hi;
-            b2i_slab_local_band(p, r, &lo, &hi);
-            g.rows.rowstart[r] = start;
-            g.rows.lo[r] = lo;
-            g.rows.gap[r] = hi - lo;
-            start += p->nyl - (hi - lo);
+            int start = 0;
+            for (int r = 0; r < p->nranks; ++r) {
+                int lo, hi;
+                b2i_slab_local_band(p, r, &lo, &hi);
+                g.rows.rowstart[r] = start;
+                g.rows.lo[r] = lo;
+                g.rows.gap[r] = hi - lo;
+                start += p->nyl - (hi - lo);
+            }
         }
         if (dir > 0) g.map_load = 1; else g.map_store = 1;
     }
