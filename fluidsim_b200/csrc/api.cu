@@ -184,6 +184,11 @@ extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double
 
 extern "C" int b2_plan_destroy(b2_plan* p) {
     if (!p) return 0;
+    if (p->streams_ready) {
+        cudaStreamDestroy(p->sy1); cudaStreamDestroy(p->sx); cudaStreamDestroy(p->sy2);
+        cudaEventDestroy(p->ev_begin); cudaEventDestroy(p->ev_end);
+        for (int i = 0; i < 32; ++i) { cudaEventDestroy(p->ev_y[i]); cudaEventDestroy(p->ev_x[i]); }
+    }
     cudaFree(p->twy);
     cudaFree(p->tw0); cudaFree(p->tw1); cudaFree(p->tw2);
     cudaFree(p->k0); cudaFree(p->k1); cudaFree(p->kx);

@@ -54,7 +54,7 @@ def test_fft3d_matches_scipy(shape):
     assert rel_err(kh, kr) < 1e-14
 
 
-@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (64, 1024), (2048, 512), (15, 24), (11, 9)])
+@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (64, 1024), (2048, 512), (16, 2048), (15, 24), (11, 9)])
 def test_fft2d_matches_scipy(shape):
     torch = _torch()
     from fluidsim_b200.fft import FFT2DWithB200
@@ -354,3 +354,15 @@ def test_512_properties_fft_roundtrip_energy_and_pruning():
     assert float((a - S).abs().max()) <= 1e-13 * float(a.abs().max())
     assert float(oper.divfft_from_vecfft(S[0], S[1], S[2]).abs().max()) < 1e-10
     assert float(S[0][oper.where_dealiased.bool()].abs().max()) == 0.0
+
+
+def test_longest_lines_2048_fused_against_oracle():
+    """Line length 2048 (largest supported) through the fused path: ns2d with nx = 2048 (x pass) and
+    ns2d with ny = 2048 (y pass), and a thin ns3d grid with nz = 2048 (z pass)."""
+    for shape in ((2048, 16), (16, 2048)):
+        meta = dict(solver="ns2d", shape=shape, params=dict(nu_2=1e-3, deltat0=1e-3, Lx=8.0, Ly=8.0))
+        o, sim, worst = _run_both(meta, 3, "init_noise")
+        assert worst < 1e-10, (shape, worst)
+    meta = dict(solver="ns3d", shape=(16, 8, 2048), params=dict(nu_2=1e-3, deltat0=1e-3))
+    o, sim, worst = _run_both(meta, 3, "init_noise")
+    assert worst < 1e-10, worst
