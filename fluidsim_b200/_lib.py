@@ -67,6 +67,7 @@ SIGNATURES = {
     "b2_set_buffers": [_p, _p, _p, _p],
     "b2_tendencies": [_p, _p, _p, _p],
     "b2_time_step": [_p, _i, _d, _p, _p],
+    "b2_time_step_cfl": [_p, _i, _d, _d, _p, _p, _p, _p],
     "b2_plan_create_slab": [C.POINTER(_p), _i, _i, _i, _d, _d, _d, _i, _i, _i],
     "b2_slab_kept_rows": [_p, C.POINTER(_i)],
     "b2_slab_set_buffers": [_p, _p, _p],

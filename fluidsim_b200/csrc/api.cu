@@ -942,6 +942,7 @@ struct RKArgs {
     const uint8_t* mask;
     long long fsize;
     double dt, N2;
+    const double* dt_ptr;  // device-resident time increment (CFL steps); overrides dt when set
 };
 
 // Epilogue of a stage: raw FFT(v x omega) -> (+ buoyancy terms) -> Leray projection -> dealiasing
@@ -983,7 +984,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
             for (int v = 0; v < NV; ++v) a.Tout[v * a.fsize + i] = T[v];
             continue;
         }
-        const double dt = a.dt;
+        const double dt = a.dt_ptr ? *a.dt_ptr : a.dt;
         double E = 1.0, E2 = 1.0;
         if (MODE != M_RK4_3) {
             const double fd = freq_diss(a.visc, K2, origin);
@@ -1106,7 +1107,7 @@ static int ensure_streams(b2_plan* p) {
 }
 
 // raw nonlinear term of stage input `Sin` into work[0..nout-1] (scaled FFT, not yet projected)
-static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream_t s) {
+static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream_t s, double* vmax = nullptr) {
     int nwork, nvar;
     if (b2_work_fields(p, p->solver, &nwork, &nvar)) return -1;
     const long long fs = p->fsize();
@@ -1151,7 +1152,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
             {
                 ProfScope ps(PC_X_FUSED, p->sx);
                 if ((e = b2i_xpass_fused(p, W, (long long)(z1 - z0) * p->n1, scale, nkeep, p->nk,
-                                         (long long)z0 * p->n1, p->sx)))
+                                         (long long)z0 * p->n1, p->sx, vmax)))
                     return e;
             }
             CUDA_TRY(cudaEventRecord(p->ev_x[c], p->sx));
@@ -1171,7 +1172,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
         }
         {
             ProfScope ps(PC_X_FUSED, s);
-            if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, p->nk, 0, s))) return e;
+            if ((e = b2i_xpass_fused(p, W, (long long)p->n0 * p->n1, scale, nkeep, p->nk, 0, s, vmax))) return e;
         }
         {
             ProfScope ps(PC_Y_FWD, s);
@@ -1209,6 +1210,7 @@ static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     a.mask = p->mask;
     a.fsize = p->fsize();
     a.dt = dt;
+    a.dt_ptr = nullptr;
     a.N2 = p->N * p->N;
     a.fcor = p->has_f ? p->f : 0.0;
     return a;
@@ -1251,6 +1253,49 @@ extern "C" int b2_time_step(b2_plan* p, int scheme, double dt, double* S_, void*
         return 0;
     }
     return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
+}
+
+// ------------------------------------------------------------------------------- CFL time step
+// compute_time_increment_CLF + _compute_time_increment_CLF_from_tmp
+// (/root/reference/fluidsim/base/time_stepping/base.py:320-354) on the device: vmax[] are the
+// max |v_i| of the stage-0 physical velocity (side output of the fused x pass).
+__global__ void cfl_dt_kernel(double* vmax, double inv_dx, double inv_dy, double inv_dz, double cfl,
+                              double dt_max, double* dt) {
+    const double tmp = vmax[0] * inv_dx + vmax[1] * inv_dy + vmax[2] * inv_dz;
+    const double dt_cfl = tmp > 0.0 ? cfl / tmp : dt_max;
+    const double maybe_new_dt = dt_cfl < dt_max ? dt_cfl : dt_max;
+    const double normalize_diff = fabs(*dt - maybe_new_dt) / maybe_new_dt;
+    if (normalize_diff > 0.02) *dt = maybe_new_dt;
+    vmax[0] = vmax[1] = vmax[2] = 0.0;
+}
+
+// One step with the CFL time increment decided on the device: dt_dev (in/out, device double) holds
+// the current deltat; vmax_dev = 3 device doubles (zeroed by the caller once).  The max |v| come
+// from the stage-0 x pass, the new deltat is used by all RK epilogues of the step.
+extern "C" int b2_time_step_cfl(b2_plan* p, int scheme, double cfl, double deltat_max, double* dt_dev,
+                                double* vmax_dev, double* S_, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = check_fused_ready(p, true))) return e;
+    if (!dt_dev || !vmax_dev) return b2i_set_error("b2_time_step_cfl: dt_dev / vmax_dev missing");
+    if (scheme != B2_SCHEME_RK4 && scheme != B2_SCHEME_RK2)
+        return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
+    cplx* S = (cplx*)S_;
+    const int nst = scheme == B2_SCHEME_RK4 ? 4 : 2;
+    const int base_mode = scheme == B2_SCHEME_RK4 ? M_RK4_0 : M_RK2_0;
+    for (int st = 0; st < nst; ++st) {
+        const cplx* Sin = st == 0 ? S : p->stage;
+        if ((e = nonlinear_raw(p, Sin, st == 0, s, st == 0 ? vmax_dev : nullptr))) return e;
+        if (st == 0) {
+            const double idx = p->n2 / p->L2, idy = p->n1 / p->L1, idz = p->n0 > 1 ? p->n0 / p->L0 : 0.0;
+            cfl_dt_kernel<<<1, 1, 0, s>>>(vmax_dev, idx, idy, idz, cfl, deltat_max, dt_dev);
+            B2_LAUNCH_CHECK("cfl_dt_kernel");
+        }
+        RKArgs a = rk_args(p, Sin, S, 0.0);
+        a.dt_ptr = dt_dev;
+        if ((e = launch_rk_stage(p, base_mode + st, a, s))) return e;
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------------------- development hooks

@@ -68,7 +68,7 @@ int b2i_xpass_c2r(b2_plan* p, const cplx* K, double* X, cudaStream_t s);
 int b2i_xpass_r2c(b2_plan* p, const double* X, cplx* K, double scale, cudaStream_t s);
 // fused c2r -> product -> r2c for p->solver; W fields as produced by b2i_first_inverse_pass
 int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch,
-                    long long line0, cudaStream_t s);
+                    long long line0, cudaStream_t s, double* vmax = nullptr);
 void b2i_xpass_share_sm(bool on);
 // dealiased band [lo, hi) of the LOCAL ky rows of rank r (lo == hi: none), from the global band
 void b2i_slab_local_band(const b2_plan* p, int r, int* lo, int* hi);

@@ -92,7 +92,9 @@ struct ScaleStore {
 };
 
 // ------------------------------------------------------------------------------- strided pass
-template <int N, int E, int TK, int DIR, class LoadOp, class StoreOp>
+// ROWMAP: compile the RowMap row translation in (slab y passes only; it costs ~10 % when merely
+// tested at run time in the single-GPU passes).
+template <int N, int E, int TK, int DIR, bool ROWMAP, class LoadOp, class StoreOp>
 __global__ void __launch_bounds__(TK*(N / E))
     fft_strided_kernel(Geom g, LoadOp ld, StoreOp st, const cplx* __restrict__ tw) {
     extern __shared__ double b2_smem[];
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(TK*(N / E))
     for (int m = 0; m < E; ++m) {
         const int i = t + m * T;
         const bool zero = !active || (g.skip_load && i >= g.band_lo && i < g.band_hi);
-        const int il = (g.map_load && !zero) ? g.rows(i) : i;
+        int il = i;
+        if constexpr (ROWMAP) il = (g.map_load && !zero) ? g.rows(i) : i;
         x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)il * g.es, i, col, outer);
     }
     fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(TK*(N / E))
         for (int m = 0; m < E; ++m) {
             const int i = t + m * T;
             if (!(g.skip_store && i >= g.band_lo && i < g.band_hi)) {
-                const int is = g.map_store ? g.rows(i) : i;
+                int is = i;
+                if constexpr (ROWMAP) is = g.map_store ? g.rows(i) : i;
                 st(field, base + (long long)is * g.es, i, col, outer, x[m]);
             }
         }
@@ -243,11 +247,26 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
     r2c_line<N, E>(x, K + line * (M + 1), plane, t, twN, SyncBlock(), scale, active, M + 1);
 }
 
+// side output of the fused x pass: max |u| of the leading op.nvmax physical fields (the velocity),
+// accumulated with atomicMax into op.vmax[f] -- the reductions of
+// _compute_time_increment_CLF_uxuyuz (/root/reference/fluidsim/base/time_stepping/base.py:320-339)
+// at no extra pass over memory.  W = number of consecutive lanes holding one line (<= 32).
+template <int E, int W>
+B2_DEVINL void b2_line_absmax(const cplx (&x)[E], double* dst, bool wanted) {
+    double mx = 0.0;
+#pragma unroll
+    for (int m = 0; m < E; ++m) mx = fmax(mx, fmax(fabs(x[m].x), fabs(x[m].y)));
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o, W));
+    if (wanted && (threadIdx.x % W) == 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__double_as_longlong(mx));
+}
+
 // fused: NI spectral lines -> c2r -> pointwise Op -> r2c -> NO spectral lines.
 // Op: struct with static NI, NO; in[NI], out[NO] pointers (field bases);
 //     __device__ void point(const double* u /*NI*/, double* r /*NO*/) const.
 // Physical values are parked in thread-private shared-memory slots between transforms.
-template <int N, int E, int LPB, class Op>
+template <int N, int E, int LPB, bool VMAX, class Op>
 __global__ void __launch_bounds__(LPB*((N / 2) / E))
     xpass_fused_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
                        int pitch, long long line0) {
@@ -266,6 +285,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 #pragma unroll 1
     for (int f = 0; f < NI; ++f) {
         c2r_line<N, E>(x, op.in[f] + loff, plane, t, twN, SyncBlock(), nkeep);
+        if constexpr (VMAX) b2_line_absmax<E, (T < 32 ? T : 32)>(x, op.vmax + f, f < op.nvmax);
 #pragma unroll
         for (int m = 0; m < E; ++m) park[(f * E + m) * T + t] = x[m];
     }
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // the latency hiding of this pass needs (see profiles/).
 // Op additionally provides out_of_group(g), needs(g, f) and point_g(g, u): the output formed by
 // group g (chosen so that it uses the group's own register-resident field).
-template <int N, int E, int MINB, class Op>
+template <int N, int E, int MINB, bool VMAX, class Op>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
                           int pitch, long long line0) {
@@ -318,6 +338,7 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     } else {
         c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, nkeep);
     }
+    if constexpr (VMAX) b2_line_absmax<E, (T < 32 ? T : 32)>(x, op.vmax + g, g < op.nvmax);
 #pragma unroll
     for (int m = 0; m < E; ++m) park[(g * E + m) * T + t] = x[m];
     __syncthreads();

@@ -26,10 +26,10 @@ static int strided_variant() {
     return v;
 }
 
-template <int N, int E, int TK, int DIR, class L, class S>
+template <int N, int E, int TK, int DIR, bool ROWMAP, class L, class S>
 static int launch_strided_cfg(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
     constexpr size_t smem = (size_t)PlaneSize<N, TK>::value * TK * sizeof(cplx);
-    auto kern = fft_strided_kernel<N, E, TK, DIR, L, S>;
+    auto kern = fft_strided_kernel<N, E, TK, DIR, ROWMAP, L, S>;
     static bool attr_done = false;
     if (!attr_done) {
         if (smem > 48 * 1024)
@@ -80,35 +80,35 @@ struct LoadFromIn {
     }
 };
 
-template <int N, int DIR, class L, class S>
+template <int N, int DIR, bool ROWMAP, class L, class S>
 static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
     if constexpr (N == 1024) {
         // measured (profiles/r1_tuning.md): the plane-strided z pass wants 128-byte row segments
         // (TK = 8, one 512-thread CTA per SM), the y pass prefers two 256-thread CTAs (TK = 4)
         const bool zlike = g.nouter == 1 || g.wide;
         switch (strided_variant()) {
-            case 1: return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
-            case 2: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
+            case 1: return launch_strided_cfg<N, 16, 8, DIR, ROWMAP>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 16, 4, DIR, ROWMAP>(g, nf, ld, st, tw, s);
         }
-        if (zlike) return launch_strided_cfg<N, 16, 8, DIR>(g, nf, ld, st, tw, s);
-        return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
+        if (zlike) return launch_strided_cfg<N, 16, 8, DIR, ROWMAP>(g, nf, ld, st, tw, s);
+        return launch_strided_cfg<N, 16, 4, DIR, ROWMAP>(g, nf, ld, st, tw, s);
     }
     if constexpr (N == 512) {
         switch (strided_variant()) {
-            case 1: return launch_strided_cfg<N, 16, 4, DIR>(g, nf, ld, st, tw, s);
-            case 2: return launch_strided_cfg<N, 8, 8, DIR>(g, nf, ld, st, tw, s);
-            case 3: return launch_strided_cfg<N, 8, 4, DIR>(g, nf, ld, st, tw, s);
+            case 1: return launch_strided_cfg<N, 16, 4, DIR, ROWMAP>(g, nf, ld, st, tw, s);
+            case 2: return launch_strided_cfg<N, 8, 8, DIR, ROWMAP>(g, nf, ld, st, tw, s);
+            case 3: return launch_strided_cfg<N, 8, 4, DIR, ROWMAP>(g, nf, ld, st, tw, s);
         }
     }
-    return launch_strided_cfg<N, SCfg<N>::E, SCfg<N>::TK, DIR>(g, nf, ld, st, tw, s);
+    return launch_strided_cfg<N, SCfg<N>::E, SCfg<N>::TK, DIR, ROWMAP>(g, nf, ld, st, tw, s);
 }
 
-template <int DIR, class In, class S>
+template <int DIR, bool ROWMAP = false, class In, class S>
 static int launch_strided(bool fast, int N, Geom g, int nf, In in, S st, const cplx* tw, cudaStream_t s) {
     LoadFromIn<In> ld{in};
     if (fast) {
         switch (N) {
-#define B2_CASE(n) case n: return launch_strided_n<n, DIR>(g, nf, ld, st, tw, s);
+#define B2_CASE(n) case n: return launch_strided_n<n, DIR, ROWMAP>(g, nf, ld, st, tw, s);
             B2_CASE(8) B2_CASE(16) B2_CASE(32) B2_CASE(64) B2_CASE(128) B2_CASE(256) B2_CASE(512)
             B2_CASE(1024) B2_CASE(2048)
 #undef B2_CASE
@@ -375,6 +375,6 @@ int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     PlainIn ld;
     PlainStore st;
     for (int f = 0; f < nf; ++f) { ld.in[f] = in[f] + in_off; st.out[f] = out[f] + out_off; }
-    return dir < 0 ? launch_strided<-1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s)
-                   : launch_strided<+1>(p->fasty, p->gy, g, nf, ld, st, p->twy, s);
+    return dir < 0 ? launch_strided<-1, true>(p->fasty, p->gy, g, nf, ld, st, p->twy, s)
+                   : launch_strided<+1, true>(p->fasty, p->gy, g, nf, ld, st, p->twy, s);
 }

@@ -37,6 +37,8 @@ struct OpNS3D {
     static constexpr int NI = 6, NO = 3;
     const cplx* in[NI];
     cplx* out[NO];
+    double* vmax;  // optional max|u| side output (CFL), nvmax leading fields
+    int nvmax;
     B2_DEVINL void point(const double* u, double* r) const {
         r[0] = u[1] * u[5] - u[2] * u[4];
         r[1] = u[2] * u[3] - u[0] * u[5];
@@ -60,6 +62,8 @@ struct OpStrat {
     static constexpr int NI = 7, NO = 6;
     const cplx* in[NI];
     cplx* out[NO];
+    double* vmax;  // optional max|u| side output (CFL), nvmax leading fields
+    int nvmax;
     B2_DEVINL void point(const double* u, double* r) const {
         r[0] = u[1] * u[5] - u[2] * u[4];
         r[1] = u[2] * u[3] - u[0] * u[5];
@@ -88,6 +92,8 @@ struct OpNS2D {
     static constexpr int NI = 4, NO = 1;
     const cplx* in[NI];
     cplx* out[NO];
+    double* vmax;  // optional max|u| side output (CFL), nvmax leading fields
+    int nvmax;
     double beta;
     B2_DEVINL void point(const double* u, double* r) const {
         r[0] = beta == 0.0 ? -u[0] * u[2] - u[1] * u[3] : -u[0] * u[2] - u[1] * (u[3] + beta);
@@ -133,14 +139,18 @@ static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double sca
     // half an SM, so that exactly one x-pass CTA plus one strided-pass CTA are co-resident per SM
     // (the x pass is L1/FP64 bound, the y passes are HBM bound: they overlap, see api.cu)
     const bool share = g_xpass_share_sm;
-    auto kern = share ? xpass_fused_fp_kernel<N, E, 2, Op> : xpass_fused_fp_kernel<N, E, 1, Op>;
+    const bool vm = op.vmax != nullptr;
+    auto kern = share ? xpass_fused_fp_kernel<N, E, 2, false, Op>
+                      : (vm ? xpass_fused_fp_kernel<N, E, 1, true, Op> : xpass_fused_fp_kernel<N, E, 1, false, Op>);
+    if (share && vm) return b2i_set_error("x pass: CFL side output is not available in SM-sharing mode");
     size_t smem_req = smem;
     if (share && smem_req < 118 * 1024) smem_req = 118 * 1024;
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[share]) {
+    static bool attr_done[3] = {false, false, false};
+    const int slot = share ? 1 : (vm ? 2 : 0);
+    if (!attr_done[slot]) {
         if (smem_req > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
-        attr_done[share] = true;
+        attr_done[slot] = true;
     }
     kern<<<(unsigned)nlines, Op::NI * T, smem_req, s>>>(op, nlines, tw, scale, nkeep, pitch, line0);
     B2_LAUNCH_CHECK("xpass_fused_fp_kernel");
@@ -158,12 +168,13 @@ static int launch_fused_n(Op op, long long nlines, const cplx* tw, double scale,
     constexpr int LPB = lpb_for(T, per_ls, 100 * 1024, 256);
     constexpr size_t smem = LPB * per_ls;
     static_assert(smem <= 227 * 1024, "x-pass tile does not fit shared memory");
-    auto kern = xpass_fused_kernel<N, E, LPB, Op>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    const bool vm = op.vmax != nullptr;
+    auto kern = vm ? xpass_fused_kernel<N, E, LPB, true, Op> : xpass_fused_kernel<N, E, LPB, false, Op>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[vm]) {
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_done = true;
+        attr_done[vm] = true;
     }
     const unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);
     kern<<<grid, LPB * T, smem, s>>>(op, nlines, tw, scale, nkeep, pitch, line0);
@@ -277,21 +288,24 @@ static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int n
 }
 
 int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch, long long line0,
-                  cudaStream_t s) {
+                    cudaStream_t s, double* vmax) {
     if (!p->fast2) return b2i_set_error("fused x pass needs a power-of-two nx");
     if (p->solver == B2_SOLVER_NS3D) {
         OpNS3D op;
+        op.vmax = vmax; op.nvmax = 3;
         for (int f = 0; f < 6; ++f) op.in[f] = W[f];
         for (int f = 0; f < 3; ++f) op.out[f] = W[f];
         return launch_fused(p, op, nlines, scale, nkeep, pitch, line0, s);
     }
     if (p->solver == B2_SOLVER_NS3D_STRAT) {
         OpStrat op;
+        op.vmax = vmax; op.nvmax = 3;
         for (int f = 0; f < 7; ++f) op.in[f] = W[f];
         for (int f = 0; f < 6; ++f) op.out[f] = W[f];
         return launch_fused(p, op, nlines, scale, nkeep, pitch, line0, s);
     }
     OpNS2D op;
+    op.vmax = vmax; op.nvmax = 2;
     for (int f = 0; f < 4; ++f) op.in[f] = W[f];
     op.out[0] = W[0];
     op.beta = p->beta;

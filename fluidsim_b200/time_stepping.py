@@ -106,6 +106,8 @@ class TimeSteppingPseudoSpectralB200:
         self.deltat = params_ts.deltat0
         self.deltat_max = params_ts.deltat_max
         self._maxbuf = torch.zeros(1, dtype=torch.float64, device=self.sim.oper.device)
+        self._dt_dev = None
+        self._vmax_dev = None
 
     def _init_time_scheme(self):
         type_time_scheme = self.params.time_stepping.type_time_scheme
@@ -165,8 +167,8 @@ class TimeSteppingPseudoSpectralB200:
         return self.it >= self.params.time_stepping.it_end
 
     def one_time_step(self):
-        if self.params.time_stepping.USE_CFL:
-            self.compute_time_increment_CLF()
+        if self.params.time_stepping.USE_CFL and not self.fused:
+            self.compute_time_increment_CLF()  # fused path: decided on the device inside the step
         if self.max_elapsed is not None and time() > self._time_should_stop:
             self._has_to_stop = True
         if self._stop_signal_received:
@@ -186,10 +188,25 @@ class TimeSteppingPseudoSpectralB200:
             sim._ensure_fused_buffers()
             prune = sim.use_pruning and sim._state_dealiased and sim._fused_mask is not None
             call("b2_set_pruning", sim.oper.plan.handle, 1 if prune else 0)
-            call(
-                "b2_time_step", sim.oper.plan.handle, self._scheme_id, float(self.deltat),
-                ptr(state_spect.tensor), stream_ptr(),
-            )
+            if self.params.time_stepping.USE_CFL:
+                # CFL on the device: max|v| from the stage-0 x pass -> deltat (2 % hysteresis) ->
+                # RK epilogues; only the new deltat (one double) comes back to the host
+                if self._dt_dev is None:
+                    self._dt_dev = torch.full((1,), float(self.deltat), dtype=torch.float64, device=sim.oper.device)
+                    self._vmax_dev = torch.zeros(3, dtype=torch.float64, device=sim.oper.device)
+                else:
+                    self._dt_dev.fill_(float(self.deltat))
+                call(
+                    "b2_time_step_cfl", sim.oper.plan.handle, self._scheme_id, float(self.CFL),
+                    float(self.deltat_max), ptr(self._dt_dev), ptr(self._vmax_dev),
+                    ptr(state_spect.tensor), stream_ptr(),
+                )
+                self.deltat = float(self._dt_dev.item())
+            else:
+                call(
+                    "b2_time_step", sim.oper.plan.handle, self._scheme_id, float(self.deltat),
+                    ptr(state_spect.tensor), stream_ptr(),
+                )
         else:
             self._time_step_RK()
             if sim.ndim == 3:

@@ -176,6 +176,13 @@ int b2_slab_phase_b(b2_plan* p, void* stream);
 int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S,
                     double* T_out, void* stream);
 
+/* one step with the CFL time increment (base/time_stepping/base.py:320-354) decided on the device:
+ * the max |v_i| are a side output of the stage-0 fused x pass (no extra pass over memory, no
+ * state_phys), dt_dev (device double, in/out) carries deltat with the 2 % hysteresis, vmax_dev = 3
+ * device doubles zeroed once by the caller. */
+int b2_time_step_cfl(b2_plan* p, int scheme, double cfl, double deltat_max, double* dt_dev,
+                     double* vmax_dev, double* S, void* stream);
+
 /* kernels launched by this library since load (for bench.py's gpu_launches) */
 long long b2_launch_count(void);
 
