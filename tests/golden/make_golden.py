@@ -30,6 +30,9 @@ CASES = {
     "ns3d_20x15x10_rk4_spherical": ("ns3d", (20, 15, 10), 3, dict(nu_2=5e-3, nu_m4=1e-3, deltat0=2e-2, truncation_shape="spherical")),
     "strat_16x16x16_rk4": ("ns3d.strat", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2, N=2.0)),
     "strat_16x8x32_rk2": ("ns3d.strat", (16, 8, 32), 4, dict(nu_4=1e-3, deltat0=1e-2, N=0.5, f=0.3, type_time_scheme="RK2")),
+    "ns3d_16x16x16_rk4_spherical": ("ns3d", (16, 16, 16), 4, dict(nu_2=5e-3, deltat0=2e-2, truncation_shape="spherical", coef_dealiasing=0.8)),
+    "ns3d_32x16x16_rk2_nomultalias": ("ns3d", (32, 16, 16), 4, dict(nu_4=1e-4, deltat0=1e-2, type_time_scheme="RK2", truncation_shape="no_multiple_aliases", coef_dealiasing=0.9, Lx=8.0)),
+    "strat_16x16x8_rk4_spherical": ("ns3d.strat", (16, 16, 8), 4, dict(nu_2=1e-2, deltat0=1e-2, N=1.5, truncation_shape="spherical")),
     "ns2d_32x32_rk4": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
     "ns2d_64x32_rk2_beta": ("ns2d", (64, 32), 5, dict(nu_2=1e-3, deltat0=1e-2, beta=0.4, type_time_scheme="RK2", Lx=8.0, Ly=8.0)),
     "ns2d_24x15_rk4_odd": ("ns2d", (24, 15), 3, dict(nu_2=1e-3, deltat0=2e-2, Lx=8.0, Ly=8.0, truncation_shape="no_multiple_aliases")),

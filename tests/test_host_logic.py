@@ -1,0 +1,99 @@
+"""CPU tests of host-side logic: slab band / split arithmetic, bench accounting, params defaults."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+class _FakeSlab:
+    """SlabSimul._local_band without a GPU (the method only uses nyl / world / cyclic)."""
+
+    def __init__(self, ny, world, cyclic):
+        self.ny, self.world, self.cyclic, self.nyl = ny, world, cyclic, ny // world
+
+
+@pytest.mark.parametrize("ny,world", [(16, 2), (16, 8), (1024, 4), (1024, 8), (64, 1)])
+@pytest.mark.parametrize("cyclic", [False, True])
+@pytest.mark.parametrize("band", [(6, 11), (342, 683), (0, 0), (3, 16)])
+def test_local_band_matches_brute_force(ny, world, cyclic, band):
+    from fluidsim_b200.slab import SlabSimul
+
+    gy_lo, gy_hi = band
+    if gy_hi > ny:
+        pytest.skip("band outside the grid")
+    if gy_lo == gy_hi:
+        gy_lo = gy_hi = ny  # "no band" convention
+    fake = _FakeSlab(ny, world, cyclic)
+    total_kept = 0
+    for r in range(world):
+        lo, hi = SlabSimul._local_band(fake, r, gy_lo, gy_hi)
+        rows = [yl * world + r if cyclic else r * fake.nyl + yl for yl in range(fake.nyl)]
+        in_band = [gy_lo <= g < gy_hi for g in rows]
+        # the local band must be exactly the set of local rows inside the global band
+        expect = [lo <= yl < hi for yl in range(fake.nyl)]
+        assert in_band == expect, (r, lo, hi)
+        total_kept += fake.nyl - (hi - lo)
+    assert total_kept == ny - (gy_hi - gy_lo)
+
+
+def test_cyclic_distribution_balances_kept_rows():
+    from fluidsim_b200.slab import SlabSimul
+
+    ny, world, band = 1024, 8, (342, 683)
+    kept = {}
+    for cyclic in (False, True):
+        fake = _FakeSlab(ny, world, cyclic)
+        kept[cyclic] = [fake.nyl - (hi - lo) for lo, hi in (SlabSimul._local_band(fake, r, *band) for r in range(world))]
+    assert max(kept[False]) == 128 and min(kept[False]) == 0  # blocks: middle ranks idle
+    assert max(kept[True]) - min(kept[True]) <= 1            # cyclic: balanced
+
+
+def test_exchanged_row_is_a_permutation():
+    from fluidsim_b200.slab import exchanged_row
+
+    for cyclic in (False, True):
+        rows = sorted(exchanged_row(i, 4, 8, cyclic) for i in range(32))
+        assert rows == list(range(32))
+
+
+def test_bench_traffic_accounting():
+    b = _bench()
+    full = b.class_passes("ns3d")
+    assert full[:5] == [12.0, 12.0, 9.0, 6.0, 6.0]
+    f = 2.0 / 3
+    pr = b.class_passes("ns3d", f, f, f)
+    assert abs(pr[2] - 9 * f) < 1e-12                      # x pass: R 6 fx + W 3 fx
+    assert abs(pr[0] - (6 * f**3 + 6 * f**2)) < 1e-12      # z-inverse: R kept box, W all z of kept columns
+    assert all(p_ <= q_ for p_, q_ in zip(pr, full))
+    assert b.class_passes("ns2d")[1] == 0.0 and b.class_passes("ns2d")[4] == 0.0
+    assert b.STEP_PASSES[("ns3d", "RK4")] == 195
+
+
+def test_default_params_have_reference_names():
+    """Attribute names consumed by the reference's hot path
+    (base/time_stepping/base.py:33-94, operators3d.py:152-205, base/solvers/pseudo_spect.py:106-132)."""
+    from fluidsim_b200.params import create_default_params
+
+    p = create_default_params("ns3d.strat")
+    for k in ("nx", "ny", "nz", "Lx", "Ly", "Lz", "coef_dealiasing", "type_fft", "truncation_shape", "NO_SHEAR_MODES"):
+        assert hasattr(p.oper, k)
+    for k in ("USE_T_END", "t_end", "it_end", "USE_CFL", "type_time_scheme", "deltat0", "deltat_max", "cfl_coef", "max_elapsed"):
+        assert hasattr(p.time_stepping, k)
+    for k in ("nu_2", "nu_4", "nu_8", "nu_m4", "f", "N", "no_vz_kz0", "projection"):
+        assert hasattr(p, k)
+    assert p.oper.coef_dealiasing == 2.0 / 3 and p.time_stepping.type_time_scheme == "RK4"
+    p2 = create_default_params("ns2d")
+    assert p2.oper.Lx == 8 and hasattr(p2, "beta")
+    with pytest.raises(ValueError):
+        create_default_params("sw1l")

@@ -270,7 +270,11 @@ def test_nan_raises_value_error():
 
 
 # ------------------------------------------------------------------ dealias-pruned transforms
-@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "ns2d_32x32_rk4"])
+@pytest.mark.parametrize(
+    "name",
+    ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "ns2d_32x32_rk4",
+     "ns3d_16x16x16_rk4_spherical", "ns3d_32x16x16_rk2_nomultalias", "strat_16x16x8_rk4_spherical"],
+)
 def test_pruned_steps_match_golden_and_unpruned(name):
     """From the second step on the fused path skips everything outside the bounding box of the
     kept modes; results must be unchanged (the skipped data are exact zeros)."""
