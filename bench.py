@@ -434,7 +434,7 @@ def own_arm(args):
         t0 = time.perf_counter()
         for _ in range(ksteps):
             S.copy_(host, non_blocking=True)
-            sim.state.mark_spect_modified()
+            sim.state.mark_spect_modified()  # host data: the stepper re-checks that it is dealiased
             ts.one_time_step()
             host.copy_(S, non_blocking=True)
             torch.cuda.synchronize()

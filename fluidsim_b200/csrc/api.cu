@@ -836,6 +836,32 @@ static int compute_mask_bounds(b2_plan* p) {
     return 0;
 }
 
+// *flag = 1 if any of the nvar fields is non-zero at a dealiased (masked) mode
+__global__ void dealiased_check_kernel(const cplx* f, long long fsize, int nvar, const uint8_t* mask,
+                                       int* flag) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fsize || !mask[i]) return;
+    for (int v = 0; v < nvar; ++v) {
+        const cplx a = f[v * fsize + i];
+        if (a.x != 0.0 || a.y != 0.0) {
+            *flag = 1;
+            return;
+        }
+    }
+}
+// Is `fields` (nvar K arrays) exactly zero wherever the mask dealiases?  Writes 0 / 1 to *flag_dev
+// (device int).  Lets the host side use the pruned transforms on a state it did not produce.
+extern "C" int b2_check_dealiased(b2_plan* p, const double* fields, int nvar, const uint8_t* mask,
+                                  int* flag_dev, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!mask) return b2i_set_error("b2_check_dealiased: no mask");
+    CUDA_TRY(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
+    const long long n = p->fsize();
+    dealiased_check_kernel<<<B2_1D_GRID(n), 0, s>>>((const cplx*)fields, n, nvar, mask, flag_dev);
+    B2_LAUNCH_CHECK("dealiased_check_kernel");
+    return 0;
+}
+
 // Dealias-pruned transforms: when on, the fused path visits only the bounding box of the modes the
 // dealiasing mask keeps (all other modes of the state, the tendencies and every intermediate are
 // exact zeros and are neither loaded, transformed nor stored).  Valid only when the state itself is

@@ -108,6 +108,7 @@ class TimeSteppingPseudoSpectralB200:
         self._maxbuf = torch.zeros(1, dtype=torch.float64, device=self.sim.oper.device)
         self._dt_dev = None
         self._vmax_dev = None
+        self._flag_dev = None
 
     def _init_time_scheme(self):
         type_time_scheme = self.params.time_stepping.type_time_scheme
@@ -186,6 +187,14 @@ class TimeSteppingPseudoSpectralB200:
         state_spect = sim.state.state_spect
         if self.fused:
             sim._ensure_fused_buffers()
+            if sim.use_pruning and not sim._state_dealiased and sim._fused_mask is not None:
+                # state written from outside: one cheap pass tells whether it is dealiased already
+                # (a few ms at 1024^3 against ~200 ms saved by the pruned transforms)
+                if self._flag_dev is None:
+                    self._flag_dev = torch.zeros(1, dtype=torch.int32, device=sim.oper.device)
+                call("b2_check_dealiased", sim.oper.plan.handle, ptr(state_spect.tensor), state_spect.nvar,
+                     ptr(sim._fused_mask), ptr(self._flag_dev), stream_ptr())
+                sim._state_dealiased = int(self._flag_dev.item()) == 0
             prune = sim.use_pruning and sim._state_dealiased and sim._fused_mask is not None
             call("b2_set_pruning", sim.oper.plan.handle, 1 if prune else 0)
             if self.params.time_stepping.USE_CFL:

@@ -126,6 +126,9 @@ int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, d
  * kept by the mask (exact: everything outside is zero).  Requires the state to be dealiased, which
  * holds after every step (solvers/ns3d/time_stepping.py:16); off by default. */
 int b2_set_pruning(b2_plan* p, int on);
+/* *flag_dev (device int) = 1 if any of the nvar fields is non-zero at a mode the mask dealiases */
+int b2_check_dealiased(b2_plan* p, const double* fields, int nvar, const uint8_t* mask, int* flag_dev,
+                       void* stream);
 /* out[0..4] = kept ranges [0,out[0]) U [out[1],n0), [0,out[2]) U [out[3],n1), kx < out[4] */
 int b2_get_pruning_bounds(const b2_plan* p, int* out);
 /* number of K-sized complex work fields the fused path needs for this solver (W), nvar of state */

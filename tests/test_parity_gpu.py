@@ -378,3 +378,27 @@ def test_longest_lines_2048_fused_against_oracle():
     meta = dict(solver="ns3d", shape=(16, 8, 2048), params=dict(nu_2=1e-3, deltat0=1e-3))
     o, sim, worst = _run_both(meta, 3, "init_noise")
     assert worst < 1e-10, worst
+
+
+def test_pruning_is_not_used_on_an_undealiased_state():
+    """A state with energy in a dealiased mode must go through the unpruned path (the reference
+    evolves such a mode for one step before removing it)."""
+    torch = _torch()
+    meta, z = load_golden("ns3d_16x16x16_rk4")
+    res = []
+    for use_pruning in (True, False):
+        sim = make_gpu_sim(meta, fused=True, mask=z["mask"])
+        sim.use_pruning = use_pruning
+        s0 = z["state0"].copy()
+        idx = tuple(np.argwhere(z["mask"] == 1)[5])
+        s0[(0,) + idx] = 0.3 + 0.1j
+        set_state(sim, s0)
+        sim.time_stepping.one_time_step()
+        res.append(sim.state.state_spect.numpy())
+    assert rel_err(res[0], res[1]) < 1e-14
+    # and a clean state written from outside is recognised as dealiased: first step already pruned
+    sim = make_gpu_sim(meta, fused=True, mask=z["mask"])
+    set_state(sim, z["state0"])
+    assert not sim._state_dealiased
+    sim.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), z["state1"]) < TOL_STEP
