@@ -322,6 +322,19 @@ def own_arm(args):
     from fluidsim_b200 import _lib
 
     hbm_peak, peak_src = peaks()
+    # memory guard: the fused path holds 15 (ns3d) / 19 (strat) K fields per GPU (27 / 35 on slab
+    # plans incl. the exchange buffers); fall back to the next smaller power of two rather than
+    # drive the box out of memory
+    size_note = None
+    if args.solver != "ns2d":
+        free_b, _total_b = torch.cuda.mem_get_info()
+        nfields = {"ns3d": 15, "ns3d.strat": 19}[args.solver] if world == 1 else {"ns3d": 27, "ns3d.strat": 35}[args.solver]
+        while args.n > 64:
+            need = (nfields + 1.5) * 16.0 * args.n * args.n * (args.n // 2 + 1) / world
+            if need < 0.92 * free_b:
+                break
+            size_note = f"requested grid did not fit {free_b / 1e9:.0f} GB of free device memory; halved"
+            args.n //= 2
     if world > 1:
         sim = make_slab_sim(args, torch, dist)
         ts = sim
@@ -489,6 +502,7 @@ def own_arm(args):
                 "workload": f"{args.solver} {args.n}^{ndim} {args.scheme} float64, noise init, nu_8=1, dt=1e-4, "
                             "USE_CFL=False (fluidsim-bench protocol; forcing off)",
                 "n": args.n,
+                "size_note": size_note,
                 "state_bytes_per_gpu": S.numel() * 16,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
                 "parallelism": "single GPU" if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all)",
