@@ -322,15 +322,14 @@ def own_arm(args):
     from fluidsim_b200 import _lib
 
     hbm_peak, peak_src = peaks()
-    # memory guard: the fused path holds 15 (ns3d) / 19 (strat) K fields per GPU (27 / 35 on slab
-    # plans incl. the exchange buffers); fall back to the next smaller power of two rather than
-    # drive the box out of memory
+    # memory guard (single GPU): the fused path holds 15 (ns3d) / 19 (strat) K fields; fall back to
+    # the next smaller power of two rather than drive the box out of memory
     size_note = None
-    if args.solver != "ns2d":
+    if args.solver != "ns2d" and world == 1:  # (slab runs split the same grid: less memory per GPU)
         free_b, _total_b = torch.cuda.mem_get_info()
-        nfields = {"ns3d": 15, "ns3d.strat": 19}[args.solver] if world == 1 else {"ns3d": 27, "ns3d.strat": 35}[args.solver]
+        nfields = {"ns3d": 15, "ns3d.strat": 19}[args.solver]
         while args.n > 64:
-            need = (nfields + 1.5) * 16.0 * args.n * args.n * (args.n // 2 + 1) / world
+            need = (nfields + 1.5) * 16.0 * args.n * args.n * (args.n // 2 + 1)
             if need < 0.92 * free_b:
                 break
             size_note = f"requested grid did not fit {free_b / 1e9:.0f} GB of free device memory; halved"
