@@ -145,12 +145,79 @@ struct PlainIn {
 };
 
 // ------------------------------------------------------------------------------- x pass pieces
+// ---- experimental (off by default, knob B2_XTWC): pre/post-processing twiddles from ONE table entry
+// per thread: exp(-2 pi i (t + m T)/N) = tw[t] * exp(-i pi m / E), the second factor being a
+// compile-time constant (multiples of pi/16).  Not yet measured on the GPU (profiles/r1_tuning.md).
+constexpr double b2_cos16_ce(int j) {
+    return j == 0 ? 1.0 : j == 1 ? 0.98078528040323044913 : j == 2 ? 0.92387953251128675613
+         : j == 3 ? 0.83146961230254523708 : j == 4 ? 0.70710678118654752440
+         : j == 5 ? 0.55557023301960222474 : j == 6 ? 0.38268343236508977173
+         : j == 7 ? 0.19509032201612826785 : j == 8 ? 0.0 : -b2_cos16_ce(16 - j);
+}
+template <int J>
+struct B2C16 {  // constant-evaluated: usable as immediates in device code
+    static constexpr double c = b2_cos16_ce(J);
+    static constexpr double s = J <= 8 ? b2_cos16_ce(8 - J) : b2_cos16_ce(J - 8);
+};
+template <int N, int E, int m>
+B2_DEVINL void c2r_pre_twc(cplx (&x)[E], const cplx* __restrict__ K, int t, cplx wt, int nkeep) {
+    if constexpr (m < E) {
+        constexpr int M = N / 2, T = M / E;
+        const cplx zero = make_double2(0.0, 0.0);
+        const int k = t + m * T;
+        const cplx a = k < nkeep ? K[k] : zero;
+        const cplx b = M - k < nkeep ? K[M - k] : zero;
+        if (k == 0) {
+            x[m] = make_double2(a.x + b.x, a.x - b.x);
+        } else {
+            const cplx s = make_double2(a.x + b.x, a.y - b.y);
+            const cplx d = make_double2(a.x - b.x, a.y + b.y);
+            constexpr double cm = B2C16<m*(16 / E)>::c, sm = B2C16<m*(16 / E)>::s;
+            // exp(+2 pi i k / N) = conj(wt) * (cm + i sm)
+            const cplx w = make_double2(wt.x * cm + wt.y * sm, wt.x * sm - wt.y * cm);
+            const cplx e = cmul(d, w);
+            x[m] = make_double2(s.x - e.y, s.y + e.x);
+        }
+        c2r_pre_twc<N, E, m + 1>(x, K, t, wt, nkeep);
+    }
+}
+template <int N, int E, int m>
+B2_DEVINL void r2c_post_twc(const cplx (&x)[E], cplx* __restrict__ K, const cplx* plane, int t, cplx wt,
+                            double scale, bool do_store, int nkeep) {
+    if constexpr (m < E) {
+        constexpr int M = N / 2, T = M / E;
+        const int k = t + m * T;
+        if (k == 0) {
+            if (do_store) {
+                K[0] = make_double2((x[m].x + x[m].y) * scale, 0.0);
+                if (M < nkeep) K[M] = make_double2((x[m].x - x[m].y) * scale, 0.0);
+            }
+        } else {
+            const cplx zc = cconj(plane[b2_pad<1>(M - k)]);
+            const cplx s = cadd(x[m], zc);
+            const cplx d = csub(x[m], zc);
+            constexpr double cm = B2C16<m*(16 / E)>::c, sm = B2C16<m*(16 / E)>::s;
+            // exp(-2 pi i k / N) = wt * (cm - i sm)
+            const cplx w = make_double2(wt.x * cm + wt.y * sm, wt.y * cm - wt.x * sm);
+            const cplx e = cmul(d, w);
+            const double hs = 0.5 * scale;
+            if (do_store && k < nkeep) K[k] = make_double2((s.x + e.y) * hs, (s.y - e.x) * hs);
+        }
+        r2c_post_twc<N, E, m + 1>(x, K, plane, t, wt, scale, do_store, nkeep);
+    }
+}
+
 // c2r along a contiguous line of N reals (M = N/2 complex FFT).  On exit x[m] = (u[2n], u[2n+1]),
 // n = t + m*T.  Unnormalised (FFTW c2r convention).  Imaginary parts of k=0 and k=N/2 are ignored.
-template <int N, int E, class Sync>
+template <int N, int E, bool TWC = false, class Sync>
 B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, cplx* plane, int t,
                         const cplx* __restrict__ twN, Sync sync, int nkeep) {
     constexpr int M = N / 2, T = M / E;
+    if constexpr (TWC) {
+        c2r_pre_twc<N, E, 0>(x, K, t, __ldg(twN + t), nkeep);
+        fft_line<M, E, +1, 1, 2>(x, plane, t, 0, twN, sync);
+        return;
+    }
     const cplx zero = make_double2(0.0, 0.0);
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -173,7 +240,7 @@ B2_DEVINL void c2r_line(cplx (&x)[E], const cplx* __restrict__ K, cplx* plane, i
 }
 
 // r2c: x[m] = (u[2n], u[2n+1]) on entry; writes K[0..M] scaled by `scale`.
-template <int N, int E, class Sync>
+template <int N, int E, bool TWC = false, class Sync>
 B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
                         const cplx* __restrict__ twN, Sync sync, double scale, bool do_store, int nkeep) {
     constexpr int M = N / 2, T = M / E;
@@ -182,6 +249,10 @@ B2_DEVINL void r2c_line(cplx (&x)[E], cplx* __restrict__ K, cplx* plane, int t,
 #pragma unroll
     for (int m = 0; m < E; ++m) plane[b2_pad<1>(t + m * T)] = x[m];
     sync();
+    if constexpr (TWC) {
+        r2c_post_twc<N, E, 0>(x, K, plane, t, __ldg(twN + t), scale, do_store, nkeep);
+        return;
+    }
     const double hs = 0.5 * scale;
 #pragma unroll
     for (int m = 0; m < E; ++m) {
@@ -319,7 +390,7 @@ __global__ void __launch_bounds__(LPB*((N / 2) / E))
 // the latency hiding of this pass needs (see profiles/).
 // Op additionally provides out_of_group(g), needs(g, f) and point_g(g, u): the output formed by
 // group g (chosen so that it uses the group's own register-resident field).
-template <int N, int E, int MINB, bool VMAX, class Op>
+template <int N, int E, int MINB, bool VMAX, class Op, bool TWC = false>
 __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     xpass_fused_fp_kernel(Op op, long long nlines, const cplx* __restrict__ twN, double scale, int nkeep,
                           int pitch, long long line0) {
@@ -334,9 +405,9 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     const long long loff = line * pitch;
     cplx x[E];
     if constexpr (T <= 32) {
-        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncWarp(), nkeep);
+        c2r_line<N, E, TWC>(x, op.in[g] + loff, plane, t, twN, SyncWarp(), nkeep);
     } else {
-        c2r_line<N, E>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, nkeep);
+        c2r_line<N, E, TWC>(x, op.in[g] + loff, plane, t, twN, SyncNamed<T>{g + 1}, nkeep);
     }
     if constexpr (VMAX) b2_line_absmax<E, (T < 32 ? T : 32)>(x, op.vmax + g, g < op.nvmax);
 #pragma unroll
@@ -359,9 +430,9 @@ __global__ void __launch_bounds__(Op::NI*((N / 2) / E), MINB)
     }
     cplx* const outp = op.out[op.out_of_group(g)] + loff;
     if constexpr (T <= 32) {
-        r2c_line<N, E>(x, outp, plane, t, twN, SyncWarp(), scale, true, nkeep);
+        r2c_line<N, E, TWC>(x, outp, plane, t, twN, SyncWarp(), scale, true, nkeep);
     } else {
-        r2c_line<N, E>(x, outp, plane, t, twN, SyncNamed<T>{g + 1}, scale, true, nkeep);
+        r2c_line<N, E, TWC>(x, outp, plane, t, twN, SyncNamed<T>{g + 1}, scale, true, nkeep);
     }
 }
 

@@ -140,13 +140,17 @@ static int launch_fused_fp_n(Op op, long long nlines, const cplx* tw, double sca
     // (the x pass is L1/FP64 bound, the y passes are HBM bound: they overlap, see api.cu)
     const bool share = g_xpass_share_sm;
     const bool vm = op.vmax != nullptr;
+    // experimental, off by default: B2_XTWC=1 selects the computed pre/post twiddle variant
+    static const bool twc = getenv("B2_XTWC") != nullptr;
     auto kern = share ? xpass_fused_fp_kernel<N, E, 2, false, Op>
-                      : (vm ? xpass_fused_fp_kernel<N, E, 1, true, Op> : xpass_fused_fp_kernel<N, E, 1, false, Op>);
+                      : (vm ? xpass_fused_fp_kernel<N, E, 1, true, Op>
+                            : (twc ? xpass_fused_fp_kernel<N, E, 1, false, Op, true>
+                                   : xpass_fused_fp_kernel<N, E, 1, false, Op>));
     if (share && vm) return b2i_set_error("x pass: CFL side output is not available in SM-sharing mode");
     size_t smem_req = smem;
     if (share && smem_req < 118 * 1024) smem_req = 118 * 1024;
-    static bool attr_done[3] = {false, false, false};
-    const int slot = share ? 1 : (vm ? 2 : 0);
+    static bool attr_done[4] = {false, false, false, false};
+    const int slot = share ? 1 : (vm ? 2 : (twc ? 3 : 0));
     if (!attr_done[slot]) {
         if (smem_req > 48 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
