@@ -147,7 +147,7 @@ struct PlainIn {
 // ------------------------------------------------------------------------------- x pass pieces
 // ---- experimental (off by default, knob B2_XTWC): pre/post-processing twiddles from ONE table entry
 // per thread: exp(-2 pi i (t + m T)/N) = tw[t] * exp(-i pi m / E), the second factor being a
-// compile-time constant (multiples of pi/16).  Not yet measured on the GPU (profiles/r1_tuning.md).
+// compile-time constant (multiples of pi/16).  Measured: no gain (profiles/r1_tuning.md).
 constexpr double b2_cos16_ce(int j) {
     return j == 0 ? 1.0 : j == 1 ? 0.98078528040323044913 : j == 2 ? 0.92387953251128675613
          : j == 3 ? 0.83146961230254523708 : j == 4 ? 0.70710678118654752440
