@@ -78,3 +78,35 @@ def test_oracle_equals_reference_code(solver, shape, kw):
         a = ref.step()
         b = np.array(o.one_time_step())
         assert np.array_equal(a, b)
+
+
+def test_spectrum3d_sums_to_energy():
+    """Shell spectrum (restated fluidfft compute_3dspectrum): sum(E(k)) * deltak == energy."""
+    o = step_np.OracleSim("ns3d", 16, 12, 10, nu_2=1e-2, Lx=5.0)
+    o.init_noise()
+    spec = o.compute_spectrum3d()
+    assert abs(spec.sum() * o.oper.deltak - o.compute_energy()) < 1e-13 * o.compute_energy()
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+def test_cfl_rule_equals_reference_code():
+    """oracle CFL time increment == the reference's own _compute_time_increment_CLF_uxuyuz /
+    _compute_time_increment_CLF_from_tmp (base/time_stepping/base.py:320-354) on the same state."""
+    refshim.install()
+    from fluidsim.base.time_stepping.base import TimeSteppingBase
+
+    o = step_np.OracleSim("ns3d", 16, 12, 8, nu_2=1e-2, deltat0=0.2)
+    o.init_noise()
+    ts = TimeSteppingBase.__new__(TimeSteppingBase)
+    ts.CFL = 1.0
+    ts.deltat_max = 0.2
+    ts.deltat = 0.2
+    phys = o.state_phys
+    ts.sim = type("S", (), {})()
+    ts.sim.oper = o.oper
+    ts.sim.state = type("St", (), {"get_var": staticmethod(lambda key: phys.get_var(key))})()
+    for _ in range(3):
+        ts._compute_time_increment_CLF_uxuyuz()
+        dt_o = o.compute_time_increment_CFL(cfl=1.0, deltat_max=0.2)
+        assert ts.deltat == dt_o
+        o.one_time_step()
