@@ -190,6 +190,39 @@ B2_DEVINL void twiddle_powers(cplx w1, cplx* w) {
     }
 }
 
+// v[m] *= w1^m, m = 1..r-1.  Radix 16 forms the powers in groups of four (w^4, w^8, w^12 times
+// w^1..w^3) so that only six twiddles are live at a time (register pressure of the paired x pass).
+template <int r>
+B2_DEVINL void apply_twiddles(cplx* v, cplx w1) {
+    if constexpr (r <= 8) {
+        cplx w[r > 1 ? r : 2];
+        twiddle_powers<r>(w1, w);
+#pragma unroll
+        for (int m = 1; m < r; ++m) v[m] = cmul(v[m], w[m]);
+    } else {
+        static_assert(r == 16, "radix");
+        const cplx w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+        v[1] = cmul(v[1], w1);
+        v[2] = cmul(v[2], w2);
+        v[3] = cmul(v[3], w3);
+        const cplx w4 = cmul(w2, w2);
+        v[4] = cmul(v[4], w4);
+        v[5] = cmul(v[5], cmul(w4, w1));
+        v[6] = cmul(v[6], cmul(w4, w2));
+        v[7] = cmul(v[7], cmul(w4, w3));
+        const cplx w8 = cmul(w4, w4);
+        v[8] = cmul(v[8], w8);
+        v[9] = cmul(v[9], cmul(w8, w1));
+        v[10] = cmul(v[10], cmul(w8, w2));
+        v[11] = cmul(v[11], cmul(w8, w3));
+        const cplx w12 = cmul(w8, w4);
+        v[12] = cmul(v[12], w12);
+        v[13] = cmul(v[13], cmul(w12, w1));
+        v[14] = cmul(v[14], cmul(w12, w2));
+        v[15] = cmul(v[15], cmul(w12, w3));
+    }
+}
+
 // Stockham stages.  TWS = stride in the twiddle table (table holds exp(-2 pi i k / (N*TWS))).
 // Twiddles: one table load (w^1) per butterfly, higher powers by multiplication -- the table
 // gathers of a per-element lookup saturate the L1/LSU pipe (profiles/README.md).
@@ -210,10 +243,7 @@ struct FftStages {
                 const int jm = (t + q * T) & (Ns - 1);
                 cplx w1 = __ldg(tw + (size_t)jm * (TWS * (N / (Ns * r))));
                 if (DIR > 0) w1.y = -w1.y;
-                cplx w[r > 1 ? r : 2];
-                twiddle_powers<r>(w1, w);
-#pragma unroll
-                for (int m = 1; m < r; ++m) v[m] = cmul(v[m], w[m]);
+                apply_twiddles<r>(v, w1);
             }
             Bfly<r, DIR>::run(v);
 #pragma unroll

@@ -3,6 +3,7 @@
 
 #include "internal.h"
 #include "passes.cuh"
+#include "xpair_op.h"
 
 static bool g_xpass_share_sm = false;
 void b2i_xpass_share_sm(bool on) { g_xpass_share_sm = on; }
@@ -294,6 +295,19 @@ static int launch_fused(b2_plan* p, Op op, long long nlines, double scale, int n
 int b2i_xpass_fused(b2_plan* p, cplx* const* W, long long nlines, double scale, int nkeep, int pitch, long long line0,
                     cudaStream_t s, double* vmax) {
     if (!p->fast2) return b2i_set_error("fused x pass needs a power-of-two nx");
+    static const bool use_old = getenv("B2_XPASS_OLD") != nullptr;  // development: round-1 kernels for A/B runs
+    if (!use_old) {
+        PairOp op;
+        op.vmax = vmax;
+        op.beta = p->beta;
+        const int nin = p->solver == B2_SOLVER_NS3D ? 6 : (p->solver == B2_SOLVER_NS3D_STRAT ? 7 : 4);
+        const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
+        for (int f = 0; f < 7; ++f) op.in[f] = W[f < nin ? f : 0];
+        for (int f = 0; f < 6; ++f) op.out[f] = W[f < nout ? f : 0];
+        if (p->solver == B2_SOLVER_NS3D) return b2i_xpair_ns3d(p, op, nlines, scale, nkeep, pitch, line0, s);
+        if (p->solver == B2_SOLVER_NS3D_STRAT) return b2i_xpair_strat(p, op, nlines, scale, nkeep, pitch, line0, s);
+        return b2i_xpair_ns2d(p, op, nlines, scale, nkeep, pitch, line0, s);
+    }
     if (p->solver == B2_SOLVER_NS3D) {
         OpNS3D op;
         op.vmax = vmax; op.nvmax = 3;
