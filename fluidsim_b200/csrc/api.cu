@@ -798,16 +798,30 @@ __global__ void mask_bounds_kernel(const uint8_t* mask, int n0, int n1, int nk, 
 }
 
 static void kept_range(const std::vector<int>& keep, int n, int* lo, int* hi) {
-    // [lo, hi) = smallest index interval containing every fully dealiased index, so that the kept
-    // indices are contained in [0, lo) U [hi, n)
-    int first = -1, last = -1;
-    for (int i = 0; i < n; ++i)
-        if (!keep[i]) {
-            if (first < 0) first = i;
-            last = i;
+    // [lo, hi) = the single contiguous run of fully dealiased indices around the Nyquist index n/2
+    // (the band every truncation shape removes).  Other fully dealiased indices (ky = 0 with
+    // NO_KY0, user masks, ...) stay in the visited set [0, lo) U [hi, n), where the per-mode mask
+    // zeroes them -- treating the hull of all dealiased indices as one band would skip kept rows.
+    *lo = n; *hi = n;
+    int c = n / 2;
+    if (c >= n || keep[c]) {
+        // no band at the Nyquist index: fall back to the longest run (odd sizes, exotic masks)
+        int best = 0, bl = n, i = 0;
+        while (i < n) {
+            if (keep[i]) { ++i; continue; }
+            int j = i;
+            while (j < n && !keep[j]) ++j;
+            if (j - i > best) { best = j - i; bl = i; }
+            i = j;
         }
-    if (first < 0) { *lo = n; *hi = n; }
-    else { *lo = first; *hi = last + 1; }
+        if (best == 0) return;
+        *lo = bl; *hi = bl + best;
+        return;
+    }
+    int l = c, h = c + 1;
+    while (l > 0 && !keep[l - 1]) --l;
+    while (h < n && !keep[h]) ++h;
+    *lo = l; *hi = h;
 }
 
 static int compute_mask_bounds(b2_plan* p) {
@@ -928,13 +942,17 @@ extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, do
     p->solver = solver;
     p->nu2 = nu2; p->nu4 = nu4; p->nu8 = nu8; p->num4 = num4;
     p->has_f = has_f; p->f = f; p->N = N; p->beta = beta;
-    const bool mask_changed = p->mask != mask;
+    // the kept ranges are recomputed on every push: the caller may have edited the mask in place,
+    // or a new mask may live at the address of a freed one
     p->mask = mask;
-    if (mask_changed || !mask) {
-        p->prune = 0;
-        return compute_mask_bounds(p);
+    p->prune = 0;
+    if (p->slab) {  // slab plans: ranges agreed between the ranks (b2_slab_set_pruning)
+        p->keep0_lo = p->keep0_hi = p->n0;
+        p->keep1_lo = p->keep1_hi = p->n1;
+        p->keepx = p->nk;
+        return 0;
     }
-    return 0;
+    return compute_mask_bounds(p);
 }
 
 extern "C" int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar) {

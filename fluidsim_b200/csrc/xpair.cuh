@@ -80,6 +80,62 @@ B2_DEVINL void xp_separate_store(const cplx (&x)[E], cplx* plane, int t, Sync sy
     }
 }
 
+// ------------------------------------------------------------------------------- bulk-async staging
+// The two spectral lines of the NEXT transform are fetched with cp.async.bulk (TMA, 1-D) into a
+// per-group shared-memory buffer while the current transform runs; completion is tracked by an
+// mbarrier (transaction bytes).  The threads then combine the pair from shared memory, so the global
+// load latency never sits on the critical path of a group (ncu: long_scoreboard was the top stall).
+B2_DEVINL unsigned xp_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+B2_DEVINL void xp_mbar_init(void* mbar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(xp_smem_addr(mbar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+B2_DEVINL void xp_mbar_expect_tx(void* mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(xp_smem_addr(mbar)), "r"(bytes)
+                 : "memory");
+}
+B2_DEVINL void xp_mbar_wait(void* mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "XP_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra XP_DONE_%=;\n"
+        "bra XP_WAIT_%=;\n"
+        "XP_DONE_%=:\n"
+        "}\n" ::"r"(xp_smem_addr(mbar)),
+        "r"(parity)
+        : "memory");
+}
+B2_DEVINL void xp_bulk_g2s(void* dst, const void* src, unsigned bytes, void* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     xp_smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(xp_smem_addr(mbar))
+                 : "memory");
+}
+
+// xp_load_pair from a staged copy: a[k] at st[k], b[k] at st[nkeep + k], k < nkeep
+template <int N, int E>
+B2_DEVINL void xp_combine_staged(cplx (&x)[E], const cplx* st, int t, int nkeep, bool live) {
+    constexpr int T = N / E, H = N / 2;
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        const int j = t + m * T;
+        const bool mir = m >= E / 2;
+        const int k = mir ? N - j : j;
+        cplx av = make_double2(0.0, 0.0), bv = make_double2(0.0, 0.0);
+        if (live && k < nkeep) {
+            av = st[k];
+            bv = st[nkeep + k];
+        }
+        if (k == 0 || k == H) {
+            av.y = 0.0;
+            bv.y = 0.0;
+        }
+        x[m] = mir ? make_double2(av.x + bv.y, bv.x - av.y) : make_double2(av.x - bv.y, av.y + bv.x);
+    }
+}
+
 // max |u| of the real parts (velocity components) of a transformed pair -> atomicMax(dst)
 template <int E, int W>
 B2_DEVINL void xp_absmax_re(const cplx (&x)[E], double* dst) {
@@ -104,27 +160,75 @@ struct XPTraits {
 
 // One group of T = N/E threads processes pairs of consecutive lines.  G groups per CTA (G > 1 only
 // when T <= 32: groups are then parts of one warp and synchronise with __syncwarp()).
-template <int N, int E, int G, int KIND, bool VMAX, bool PARK0, int MAXREG>
+template <int N, int E, int G, int KIND, bool VMAX, bool PARK0, int MAXREG, bool PF>
 __global__ void __launch_bounds__(G*(N / E)) __maxnreg__(MAXREG)
     xpass_pair_kernel(PairOp op, long long nlines, const cplx* __restrict__ tw, double scale, int nkeep,
                       int pitch, long long line0, int ppg) {
     extern __shared__ double b2_smem[];
     constexpr int T = N / E, PS = PlaneSize<N, 1>::value;
     constexpr int PARK_D = XPTraits<KIND>::PARK_D + (PARK0 ? 2 : 0);
-    constexpr int PER_G = PS * 2 + PARK_D * N;  // doubles per group
+    constexpr int IPP = KIND == 0 ? 6 : (KIND == 1 ? 7 : 4);  // staged transforms per pair of lines
+    // doubles per group: [mbarrier (2)] exchange plane, thread-private parking, [staging 2 x nkeep cplx]
+    const int per_g = (PF ? 2 : 0) + PS * 2 + PARK_D * N + (PF ? 4 * nkeep : 0);
     static_assert(G == 1 || T <= 32, "several groups per CTA only when a group is part of one warp");
     using Sync = typename std::conditional<(T > 32), SyncBlock, SyncWarp>::type;
     constexpr int W = T < 32 ? T : 32;
     const Sync sync{};
     const int g = threadIdx.x / T, t = threadIdx.x % T;
-    double* gbase = b2_smem + (size_t)g * PER_G;
-    cplx* plane = reinterpret_cast<cplx*>(gbase);
-    double* park = gbase + PS * 2;                               // [PARK_D][E][T] thread-private slots
+    double* gbase = b2_smem + (size_t)g * per_g;
+    void* mbar = gbase;
+    cplx* plane = reinterpret_cast<cplx*>(gbase + (PF ? 2 : 0));
+    double* park = gbase + (PF ? 2 : 0) + PS * 2;                // [PARK_D][E][T] thread-private slots
     cplx* park0 = reinterpret_cast<cplx*>(park + XPTraits<KIND>::PARK_D * N);  // PARK0: first pair
+    cplx* stage = reinterpret_cast<cplx*>(park + PARK_D * N);    // PF: staged (a, b) lines
     const long long npairs = (nlines + 1) / 2;
-    long long pair = ((long long)blockIdx.x * G + g) * ppg;
+    const long long pair0 = ((long long)blockIdx.x * G + g) * ppg;
+    long long pair = pair0;
     if ((long long)blockIdx.x * G * ppg >= npairs) return;
     const double hs = 0.5 * scale;
+    // staged item q of this group: transform k = q % IPP of pair pair0 + q / IPP
+    auto issue = [&](int q) {
+        const int it = q / IPP, k = q - it * IPP;
+        long long pr = pair0 + it;
+        if (pr >= npairs) pr = npairs - 1;
+        const long long la = 2 * pr, lb = (2 * pr + 1 < nlines) ? 2 * pr + 1 : la;
+        const cplx *a, *b;
+        if (KIND == 1 && k == 0) {
+            a = op.in[6] + (la + line0) * pitch;
+            b = op.in[6] + (lb + line0) * pitch;
+        } else {
+            const int kk = KIND == 1 ? k - 1 : k;
+            constexpr int NP = KIND == 2 ? 2 : 3;
+            const int h = kk / NP, pp = kk - h * NP;
+            const long long off = ((h ? lb : la) + line0) * pitch;
+            a = op.in[pp] + off;
+            b = op.in[pp + NP] + off;
+        }
+        const unsigned bytes = (unsigned)nkeep * (unsigned)sizeof(cplx);
+        xp_mbar_expect_tx(mbar, 2 * bytes);
+        xp_bulk_g2s(stage, a, bytes, mbar);
+        xp_bulk_g2s(stage + nkeep, b, bytes, mbar);
+    };
+    int q = 0;
+    unsigned ph = 0;
+    if constexpr (PF) {
+        if (t == 0) xp_mbar_init(mbar, 1);
+        sync();
+        if (t == 0) issue(0);
+    }
+    // next (a + i b) spectrum of the sequence into x: staged copy (PF) or direct global loads
+    auto fetch = [&](cplx (&x)[E], const cplx* a, const cplx* b, bool live) {
+        if constexpr (PF) {
+            xp_mbar_wait(mbar, ph);
+            ph ^= 1u;
+            xp_combine_staged<N, E>(x, stage, t, nkeep, live);
+            sync();  // the staging buffer has been read by the whole group
+            ++q;
+            if (t == 0 && q < ppg * IPP) issue(q);
+        } else {
+            xp_load_pair<N, E>(x, a, b, t, live ? nkeep : 0);
+        }
+    };
 #pragma unroll 1
     for (int it = 0; it < ppg; ++it, ++pair) {
         const bool pv = pair < npairs;                      // invalid groups redo the last pair, stores off
@@ -136,7 +240,7 @@ __global__ void __launch_bounds__(G*(N / E)) __maxnreg__(MAXREG)
         if constexpr (KIND == 1) {
             // buoyancy of both lines in one transform, parked (re: line a, im: line b)
             cplx xb[E];
-            xp_load_pair<N, E>(xb, op.in[6] + offa, op.in[6] + offb, t, nkeep);
+            fetch(xb, op.in[6] + offa, op.in[6] + offb, pv);
             fft_line<N, E, +1, 1, 1>(xb, plane, t, 0, tw, sync);
             cplx* bp = reinterpret_cast<cplx*>(park);
 #pragma unroll
@@ -146,13 +250,12 @@ __global__ void __launch_bounds__(G*(N / E)) __maxnreg__(MAXREG)
         for (int h = 0; h < 2; ++h) {
             const long long off = h ? offb : offa;
             const bool lv = pv && (h == 0 || bv);
-            const int nkeep_l = lv ? nkeep : 0;  // inactive line: transform zeros (inputs may be mid-rewrite)
             cplx P0[E], P1[E];
             if constexpr (KIND == 2) {
-                xp_load_pair<N, E>(P0, op.in[0] + off, op.in[2] + off, t, nkeep_l);  // (ux, d_x rot)
+                fetch(P0, op.in[0] + off, op.in[2] + off, lv);  // (ux, d_x rot)
                 fft_line<N, E, +1, 1, 1>(P0, plane, t, 0, tw, sync);
                 if constexpr (VMAX) xp_absmax_re<E, W>(P0, op.vmax + 0);
-                xp_load_pair<N, E>(P1, op.in[1] + off, op.in[3] + off, t, nkeep_l);  // (uy, d_y rot)
+                fetch(P1, op.in[1] + off, op.in[3] + off, lv);  // (uy, d_y rot)
                 fft_line<N, E, +1, 1, 1>(P1, plane, t, 0, tw, sync);
                 if constexpr (VMAX) xp_absmax_re<E, W>(P1, op.vmax + 1);
                 const double beta = op.beta;
@@ -170,17 +273,17 @@ __global__ void __launch_bounds__(G*(N / E)) __maxnreg__(MAXREG)
                 }
             } else {
                 cplx P2[E];
-                xp_load_pair<N, E>(P0, op.in[0] + off, op.in[3] + off, t, nkeep_l);  // (vx, wx)
+                fetch(P0, op.in[0] + off, op.in[3] + off, lv);  // (vx, wx)
                 fft_line<N, E, +1, 1, 1>(P0, plane, t, 0, tw, sync);
                 if constexpr (VMAX) xp_absmax_re<E, W>(P0, op.vmax + 0);
                 if constexpr (PARK0) {
 #pragma unroll
                     for (int m = 0; m < E; ++m) park0[m * T + t] = P0[m];
                 }
-                xp_load_pair<N, E>(P1, op.in[1] + off, op.in[4] + off, t, nkeep_l);  // (vy, wy)
+                fetch(P1, op.in[1] + off, op.in[4] + off, lv);  // (vy, wy)
                 fft_line<N, E, +1, 1, 1>(P1, plane, t, 0, tw, sync);
                 if constexpr (VMAX) xp_absmax_re<E, W>(P1, op.vmax + 1);
-                xp_load_pair<N, E>(P2, op.in[2] + off, op.in[5] + off, t, nkeep_l);  // (vz, wz)
+                fetch(P2, op.in[2] + off, op.in[5] + off, lv);  // (vz, wz)
                 fft_line<N, E, +1, 1, 1>(P2, plane, t, 0, tw, sync);
                 if constexpr (VMAX) xp_absmax_re<E, W>(P2, op.vmax + 2);
                 if constexpr (PARK0) {

@@ -30,20 +30,21 @@ static int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <int N, int KIND, bool VMAX, bool PARK0, int MAXREG>
+template <int N, int KIND, bool VMAX, bool PARK0, int MAXREG, bool PF>
 static int launch_pair_cfg(const PairOp& op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch,
                            long long line0, cudaStream_t s) {
     constexpr int E = XPCfg<N>::E, G = XPCfg<N>::G, T = N / E;
     constexpr int PARK_D = XPTraits<KIND>::PARK_D + (PARK0 ? 2 : 0);
-    constexpr size_t smem = (size_t)G * (PlaneSize<N, 1>::value * 2 + PARK_D * N) * sizeof(double);
-    static_assert(smem <= 227 * 1024, "paired x pass: tile does not fit shared memory");
-    auto kern = xpass_pair_kernel<N, E, G, KIND, VMAX, PARK0, MAXREG>;
+    const size_t smem = (size_t)G * ((PF ? 2 : 0) + PlaneSize<N, 1>::value * 2 + PARK_D * N + (PF ? 4 * nkeep : 0)) *
+                        sizeof(double);
+    if (smem > 227 * 1024) return b2i_set_error("paired x pass: tile does not fit shared memory");
+    auto kern = xpass_pair_kernel<N, E, G, KIND, VMAX, PARK0, MAXREG, PF>;
     if (smem > 48 * 1024) {
         // per device (a process may drive several GPUs): cheap enough to repeat on every launch
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return b2i_set_error("xpass_pair_kernel: %s", cudaGetErrorString(ce));
     }
-    static const int ppg_env = env_int("B2_XPPG", 4);
+    static const int ppg_env = env_int("B2_XPPG", 1);
     const long long npairs = (nlines + 1) / 2;
     int ppg = ppg_env < 1 ? 1 : ppg_env;
     while (ppg > 1 && npairs / ((long long)G * ppg) < 148 * 4) ppg /= 2;  // keep the grid wide
@@ -53,20 +54,26 @@ static int launch_pair_cfg(const PairOp& op, long long nlines, const cplx* tw, d
     return 0;
 }
 
-// Variants (development knob B2_XVAR, N >= 512 only):
-//   0  everything in registers (255 registers, 4 CTAs/SM at N = 1024)
-//   1  first pair parked in thread-private shared memory, <= 200 registers (5 CTAs/SM)
-//   2  first pair parked, <= 168 registers (6 CTAs/SM)
+// N >= 512: the input lines are staged with cp.async.bulk one transform ahead (PF).  Development
+// knobs: B2_XNOPF=1 direct global loads; B2_XVAR=1 first pair parked in shared memory, <= 200 registers.
 template <int N, int KIND>
 static int launch_pair_n(const PairOp& op, long long nlines, const cplx* tw, double scale, int nkeep, int pitch,
                          long long line0, cudaStream_t s) {
     static const int var = env_int("B2_XVAR", 0);
-    if (op.vmax) return launch_pair_cfg<N, KIND, true, false, 255>(op, nlines, tw, scale, nkeep, pitch, line0, s);
-    if constexpr (KIND != 2 && N >= 512) {
-        if (var == 1) return launch_pair_cfg<N, KIND, false, true, 200>(op, nlines, tw, scale, nkeep, pitch, line0, s);
-        if (var == 2) return launch_pair_cfg<N, KIND, false, true, 168>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+    static const int nopf = env_int("B2_XNOPF", 0);
+    if constexpr (N >= 512) {
+        if (op.vmax) return launch_pair_cfg<N, KIND, true, false, 255, true>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+        if (!nopf) {
+            if constexpr (KIND != 2) {
+                if (var == 1) return launch_pair_cfg<N, KIND, false, true, 200, true>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+            }
+            return launch_pair_cfg<N, KIND, false, false, 255, true>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+        }
+        return launch_pair_cfg<N, KIND, false, false, 255, false>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+    } else {
+        if (op.vmax) return launch_pair_cfg<N, KIND, true, false, 255, false>(op, nlines, tw, scale, nkeep, pitch, line0, s);
+        return launch_pair_cfg<N, KIND, false, false, 255, false>(op, nlines, tw, scale, nkeep, pitch, line0, s);
     }
-    return launch_pair_cfg<N, KIND, false, false, 255>(op, nlines, tw, scale, nkeep, pitch, line0, s);
 }
 
 template <int KIND>

@@ -50,6 +50,13 @@ class SetOfVariables:
         self.keys = list(keys)
         self.nvar = len(self.keys)
         self.info = info
+        # optional hook called whenever a writable view is handed out or the container is written
+        # through its own methods (the state uses it to invalidate "state is dealiased", see state.py)
+        self._on_touch = None
+
+    def _touch(self):
+        if self._on_touch is not None:
+            self._on_touch()
 
     # ndarray-like surface used by the reference code paths we mirror
     @property
@@ -65,6 +72,7 @@ class SetOfVariables:
         return self.tensor.dim()
 
     def __getitem__(self, item):
+        self._touch()
         return self.tensor[item]
 
     def __setitem__(self, item, value):
@@ -72,9 +80,11 @@ class SetOfVariables:
             value = value.tensor
         elif isinstance(value, np.ndarray):
             value = torch.from_numpy(value).to(self.tensor.device)
+        self._touch()
         self.tensor[item] = value
 
     def __iadd__(self, other):
+        self._touch()
         self.tensor += other.tensor if isinstance(other, SetOfVariables) else other
         return self
 
@@ -84,6 +94,7 @@ class SetOfVariables:
 
     def get_var(self, arg):
         index = arg if isinstance(arg, int) else self.keys.index(arg)
+        self._touch()
         return self.tensor[index]
 
     def set_var(self, arg, value):
@@ -91,9 +102,11 @@ class SetOfVariables:
         self[index] = value
 
     def initialize(self, value=0):
+        self._touch()
         self.tensor.fill_(value)
 
     def fill(self, value):
+        self._touch()
         self.tensor.fill_(value)
 
     def copy(self):

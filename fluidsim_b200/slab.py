@@ -189,10 +189,32 @@ class SlabSimul:
     # ---- pruning set-up -----------------------------------------------------------------------------
     @staticmethod
     def _band(keep):
-        """[lo, hi): smallest index interval containing every non-kept index (kept_range in api.cu)."""
-        idx = np.nonzero(~np.asarray(keep, dtype=bool))[0]
+        """[lo, hi): the contiguous run of non-kept indices around n/2 (``kept_range`` in api.cu).
+
+        Only that run is pruned; other fully dealiased indices (ky = 0 with NO_KY0, custom masks)
+        stay in the visited set, where the per-mode mask zeroes them."""
+        keep = np.asarray(keep, dtype=bool)
         n = len(keep)
-        return (n, n) if idx.size == 0 else (int(idx[0]), int(idx[-1]) + 1)
+        c = n // 2
+        if c >= n or keep[c]:
+            best, bl, i = 0, n, 0
+            while i < n:
+                if keep[i]:
+                    i += 1
+                    continue
+                j = i
+                while j < n and not keep[j]:
+                    j += 1
+                if j - i > best:
+                    best, bl = j - i, i
+                i = j
+            return (n, n) if best == 0 else (bl, bl + best)
+        lo, hi = c, c + 1
+        while lo > 0 and not keep[lo - 1]:
+            lo -= 1
+        while hi < n and not keep[hi]:
+            hi += 1
+        return lo, hi
 
     def _setup_pruning(self):
         """Agree on the kept ranges between the ranks and derive the all-to-all split sizes."""

@@ -84,6 +84,12 @@ class SimulBasePseudoSpectralB200:
         call("b2_set_physics", h, SOLVER_IDS[self.short_name], *self._physics_args(), ptr(mask))
         call("b2_set_buffers", h, ptr(acc), ptr(stage), ptr(work))
 
+    def mask_modified(self):
+        """Call after editing ``oper.where_dealiased`` in place: the kept ranges of the pruned
+        transforms are recomputed and the state is re-checked before the next fused step."""
+        self._fused_mask = None
+        self._state_dealiased = False
+
     def tendencies_nonlin_fused(self, state_spect=None, old=None):
         """N(state_spect) through the fused kernels (C ABI ``b2_tendencies``)."""
         self._ensure_fused_buffers()

@@ -29,6 +29,13 @@ class StatePseudoSpectral:
             value=0.0,
             device=oper.device,
         )
+        # Any writable view of state_spect handed out through the container's own interface
+        # (get_var, indexing, set_var, initialize, +=) may be used to edit the state in place, the
+        # reference idiom.  The pruned transforms need a dealiased state, so such an access drops the
+        # "state is dealiased" knowledge; the next fused step re-establishes it with one device-side
+        # check (b2_check_dealiased).  Only raw ``state_spect.tensor`` writes need an explicit
+        # ``mark_spect_modified()``.
+        self.state_spect._on_touch = self._spect_touched
         self._state_phys = None
         self._phys_dirty = True
         self.vars_computed = {}
@@ -52,6 +59,10 @@ class StatePseudoSpectral:
             self._statephys_from_statespect()
         return self._state_phys
 
+    def _spect_touched(self):
+        self._phys_dirty = True
+        self.sim._state_dealiased = False
+
     def mark_spect_modified(self):
         """Call after writing ``state_spect`` from outside the time stepper: invalidates the lazy
         ``state_phys`` and the "state is dealiased" knowledge the pruned transforms rely on."""
@@ -59,20 +70,28 @@ class StatePseudoSpectral:
         self.sim._state_dealiased = False
 
     def statephys_from_statespect(self):
-        """base/state.py:326-332 -- deferred until ``state_phys`` is read."""
+        """base/state.py:326-332 -- deferred until ``state_phys`` is read.  Called by user code after
+        editing ``state_spect`` (reference idiom): the state may no longer be dealiased."""
         self._phys_dirty = True
+        self.sim._state_dealiased = False
 
     def _statephys_from_statespect(self):
         ifft_as_arg = self.oper.ifft_as_arg
-        for ik in range(self.state_spect.nvar):
-            ifft_as_arg(self.state_spect[ik], self._state_phys[ik])
+        for ik in range(self.state_spect.nvar):  # raw tensors: reading is not a "touch"
+            ifft_as_arg(self.state_spect.tensor[ik], self._state_phys.tensor[ik])
 
     def statespect_from_statephys(self):
-        """base/state.py:318-324."""
-        phys = self.state_phys
+        """base/state.py:318-324.  Uses the physical arrays as they are (edits made through a held
+        reference included): no lazy refresh from state_spect here."""
+        if self._state_phys is None:
+            phys = self.state_phys
+        else:
+            phys = self._state_phys
         fft_as_arg = self.oper.fft_as_arg
         for ik in range(self.state_spect.nvar):
-            fft_as_arg(phys[ik], self.state_spect[ik])
+            fft_as_arg(phys.tensor[ik], self.state_spect.tensor[ik])
+        self._phys_dirty = False
+        self.sim._state_dealiased = False
 
     def get_var(self, key):
         if key in self.keys_state_spect:
@@ -121,7 +140,7 @@ class StateNS2D(StatePseudoSpectral):
     def _statephys_from_statespect(self):
         """solvers/ns2d/state.py:95-106."""
         oper = self.oper
-        rot_fft = self.state_spect.get_var("rot_fft")
+        rot_fft = self.state_spect.tensor[0]
         ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
         oper.ifft_as_arg(rot_fft, self._state_phys.get_var("rot"))
         ifft_as_arg_destroy = oper.oper_fft.ifft_as_arg_destroy
@@ -130,7 +149,10 @@ class StateNS2D(StatePseudoSpectral):
 
     def statespect_from_statephys(self):
         """solvers/ns2d/state.py:108-113."""
-        self.oper.fft_as_arg(self.state_phys.get_var("rot"), self.state_spect.get_var("rot_fft"))
+        phys = self.state_phys if self._state_phys is None else self._state_phys
+        self.oper.fft_as_arg(phys.get_var("rot"), self.state_spect.tensor[0])
+        self._phys_dirty = False
+        self.sim._state_dealiased = False
 
     def compute_energy_phys(self):
         p = self.state_phys
@@ -138,5 +160,5 @@ class StateNS2D(StatePseudoSpectral):
 
     def compute_energy_spect(self):
         oper = self.oper
-        rot_fft = self.state_spect.get_var("rot_fft")
+        rot_fft = self.state_spect.tensor[0]
         return oper.sum_wavenumbers(0.5 * rot_fft.abs() ** 2 / oper.K2_not0)

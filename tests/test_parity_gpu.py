@@ -402,3 +402,94 @@ def test_pruning_is_not_used_on_an_undealiased_state():
     assert not sim._state_dealiased
     sim.time_stepping.one_time_step()
     assert rel_err(sim.state.state_spect.numpy(), z["state1"]) < TOL_STEP
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "strat_16x16x16_rk4", "ns2d_32x32_rk4"])
+def test_pruned_with_extra_fully_masked_rows(name):
+    """Masks whose fully dealiased indices are NOT one contiguous run (NO_KY0 / NO_SHEAR_MODES zero
+    the ky = 0 or kz = 0 rows on top of the Nyquist band, /root/reference/fluidsim/operators/
+    operators3d.py:268-278, operators2d.py): only the run around n/2 may be pruned, the kept rows
+    between the masked ones must still be transformed (kept_range)."""
+    import ctypes as C
+
+    from fluidsim_b200._lib import lib
+
+    meta, z = load_golden(name)
+    mask = z["mask"].copy()
+    if mask.ndim == 3:
+        mask[:, 0, :] = 1  # ky = 0 plane (NO_KY0-like)
+        mask[0, :, :] = 1  # kz = 0 plane (NO_SHEAR_MODES-like)
+        mask[3, :, :] = 1  # an isolated fully masked kz index
+    else:
+        mask[0, :] = 1     # ky = 0 row (NO_KY0)
+        mask[5, :] = 1
+    s0 = z["state0"].copy()
+    s0[:, mask.astype(bool)] = 0.0
+    res = []
+    for use_pruning in (True, False):
+        sim = make_gpu_sim(meta, fused=True, mask=mask)
+        sim.use_pruning = use_pruning
+        set_state(sim, s0)
+        for _ in range(3):
+            sim.time_stepping.one_time_step()
+        res.append(sim.state.state_spect.numpy())
+        if use_pruning:
+            bounds = (C.c_int * 5)()
+            lib.b2_get_pruning_bounds(sim.oper.plan.handle, bounds)
+            n_ax0 = mask.shape[0] if mask.ndim == 3 else 1
+            if mask.ndim == 3:
+                assert 0 < bounds[0] < bounds[1] <= n_ax0       # band around n/2, not [0, ...)
+            assert 0 < bounds[2] < bounds[3]
+    a, b = res
+    assert np.abs(b).max() > 0
+    assert rel_err(a, b) < 1e-13
+    assert np.abs(a[:, mask.astype(bool)]).max() == 0.0
+    # the unfused operator-level path agrees too (independent of any pruning logic)
+    sim = make_gpu_sim(meta, fused=False, mask=mask)
+    set_state(sim, s0)
+    for _ in range(3):
+        sim.time_stepping.one_time_step()
+    assert rel_err(a, sim.state.state_spect.numpy()) < 1e-11
+
+
+@pytest.mark.gpu
+def test_state_edits_through_the_reference_idioms_drop_pruning():
+    """Editing state_spect through get_var / set_var / statespect_from_statephys (reference idioms,
+    /root/reference/fluidsim/base/state.py:318-332) must invalidate the "state is dealiased"
+    knowledge: the next step re-checks on the device and runs unpruned if needed."""
+    meta, z = load_golden("ns3d_16x16x16_rk4")
+    idx = tuple(np.argwhere(z["mask"] == 1)[7])
+
+    def fresh():
+        sim = make_gpu_sim(meta, fused=True, mask=z["mask"])
+        set_state(sim, z["state0"])
+        sim.time_stepping.one_time_step()
+        assert sim._state_dealiased
+        return sim
+
+    # (a) in-place edit through a get_var view
+    sim, ref = fresh(), fresh()
+    ref.use_pruning = False
+    for s in (sim, ref):
+        v = s.state.state_spect.get_var("vx_fft")
+        v[idx] = 0.25 - 0.5j
+        assert not s._state_dealiased
+        s.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), ref.state.state_spect.numpy()) < 1e-14
+    # (b) edit of state_phys through a held reference + statespect_from_statephys
+    sim, ref = fresh(), fresh()
+    ref.use_pruning = False
+    for s in (sim, ref):
+        phys = s.state.state_phys
+        phys.tensor[0] += 0.125 * phys.tensor[1] ** 2  # puts energy in dealiased modes
+        s.state.statespect_from_statephys()
+        assert not s._state_dealiased
+        s.time_stepping.one_time_step()
+    a, b = sim.state.state_spect.numpy(), ref.state.state_spect.numpy()
+    assert rel_err(a, b) < 1e-14
+    # (c) reading state_phys does not invalidate anything
+    sim = fresh()
+    _ = sim.state.state_phys
+    _ = sim.state.compute_energy_spect()
+    assert sim._state_dealiased
