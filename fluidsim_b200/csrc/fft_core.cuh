@@ -144,8 +144,12 @@ struct Bfly<16, DIR> {
 //   TK >= 8 : the 8 lanes are 8 columns of one row -> never a conflict, no padding
 //   TK == 4 : two rows per quarter-warp -> pad so that rows r apart (r = radix) differ by an odd count
 //   TK <= 2 : lanes run along the line -> pad so that strides 8 and 16 map to distinct 16-byte groups
-template <int TK>
+// PM = 1 (TK = 4, E = 16 only): no padding, XOR swizzle of the row index instead -- the two rows a
+// quarter-warp touches differ in parity for every access of the radix-16 stages, so the plane is
+// exactly N x TK elements and can double as a TMA staging / store buffer (strided.cu).
+template <int TK, int PM = 0>
 B2_DEVINL int b2_pad(int w) {
+    if (PM == 1) return w ^ ((w >> 4) & 1);
     if (TK >= 8) return w;
     if (TK == 4) return w + (w >> 4);
     return w + (w >> 3) + (w >> 6);
@@ -226,7 +230,7 @@ B2_DEVINL void apply_twiddles(cplx* v, cplx w1) {
 // Stockham stages.  TWS = stride in the twiddle table (table holds exp(-2 pi i k / (N*TWS))).
 // Twiddles: one table load (w^1) per butterfly, higher powers by multiplication -- the table
 // gathers of a per-element lookup saturate the L1/LSU pipe (profiles/README.md).
-template <int N, int E, int DIR, int TK, int TWS, int Ns, class Sync>
+template <int N, int E, int DIR, int TK, int TWS, int Ns, class Sync, int PM = 0>
 struct FftStages {
     static B2_DEVINL void run(cplx (&x)[E], cplx* __restrict__ plane, int t, int c,
                               const cplx* __restrict__ tw, Sync sync) {
@@ -256,18 +260,18 @@ struct FftStages {
                 const int j = t + q * T;
                 const int base = (j / Ns) * (Ns * r) + (j & (Ns - 1));
 #pragma unroll
-                for (int m = 0; m < r; ++m) plane[b2_pad<TK>(base + m * Ns) * TK + c] = x[q + m * Q];
+                for (int m = 0; m < r; ++m) plane[b2_pad<TK, PM>(base + m * Ns) * TK + c] = x[q + m * Q];
             }
             sync();
 #pragma unroll
-            for (int m = 0; m < E; ++m) x[m] = plane[b2_pad<TK>(t + m * T) * TK + c];
-            FftStages<N, E, DIR, TK, TWS, Ns * r, Sync>::run(x, plane, t, c, tw, sync);
+            for (int m = 0; m < E; ++m) x[m] = plane[b2_pad<TK, PM>(t + m * T) * TK + c];
+            FftStages<N, E, DIR, TK, TWS, Ns * r, Sync, PM>::run(x, plane, t, c, tw, sync);
         }
     }
 };
 
 // x[m] holds in[t + m*T] on entry and out[t + m*T] on exit (unnormalised).
-template <int N, int E, int DIR, int TK, int TWS, class Sync>
+template <int N, int E, int DIR, int TK, int TWS, int PM = 0, class Sync>
 B2_DEVINL void fft_line(cplx (&x)[E], cplx* plane, int t, int c, const cplx* __restrict__ tw, Sync sync) {
-    FftStages<N, E, DIR, TK, TWS, 1, Sync>::run(x, plane, t, c, tw, sync);
+    FftStages<N, E, DIR, TK, TWS, 1, Sync, PM>::run(x, plane, t, c, tw, sync);
 }

@@ -57,6 +57,13 @@ struct Geom {
     RowMap rows;
     int map_load, map_store;
     int outer0;     // first outer index of this launch (chunked launches)
+    // shape of the (n0, n1, nk) complex array the pass works on (TMA tensor maps, strided_tma.cuh);
+    // dim_nk == 0: unknown -> LDG kernels only
+    int dim_nk, dim_n1, dim_n0;
+    // L2 prefetch distance in CTAs (0: off): every CTA first asks L2 for the tile of the CTA l2pf
+    // positions ahead in launch order (prefetch.global.L2: no registers, no shared memory), so that
+    // the demand loads of that CTA hit L2 instead of paying the DRAM latency
+    int l2pf;
 };
 static inline Geom geom_init() {
     Geom g;
@@ -66,16 +73,20 @@ static inline Geom geom_init() {
     g.rows.P = 0; g.rows.nyl = 1; g.rows.cyclic = 0; g.rows.shift = -1; g.map_load = 0; g.map_store = 0;
     for (int r = 0; r < B2_MAXR; ++r) { g.rows.rowstart[r] = 0; g.rows.lo[r] = 0; g.rows.gap[r] = 0; }
     g.outer0 = 0;
+    g.dim_nk = 0; g.dim_n1 = 0; g.dim_n0 = 0;
+    g.l2pf = 0;
     return g;
 }
 
 #define B2_MAXF 8
 // ------------------------------------------------------------------------------- load/store ops
+B2_DEVINL void b2_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 struct PlainLoad {
     const cplx* in[B2_MAXF];
     B2_DEVINL cplx operator()(int f, long long off, int i, int col, int outer) const {
         return in[f][off];
     }
+    B2_DEVINL void prefetch(int f, long long off, int i, int col, int outer) const { b2_prefetch_l2(in[f] + off); }
 };
 struct PlainStore {
     cplx* out[B2_MAXF];
@@ -95,8 +106,9 @@ struct ScaleStore {
 // ROWMAP: compile the RowMap row translation in (slab y passes only; it costs ~10 % when merely
 // tested at run time in the single-GPU passes).
 template <int N, int E, int TK, int DIR, bool ROWMAP, class LoadOp, class StoreOp>
-__global__ void __launch_bounds__(TK*(N / E))
-    fft_strided_kernel(Geom g, LoadOp ld, StoreOp st, const cplx* __restrict__ tw) {
+__global__ void __launch_bounds__(TK*(N / E), (TK * (N / E) <= 256 ? 2 : 1))
+    fft_strided_kernel(const __grid_constant__ Geom g, const __grid_constant__ LoadOp ld,
+                       const __grid_constant__ StoreOp st, const cplx* __restrict__ tw) {
     extern __shared__ double b2_smem[];
     constexpr int T = N / E;
     cplx* plane = reinterpret_cast<cplx*>(b2_smem);
@@ -118,6 +130,30 @@ __global__ void __launch_bounds__(TK*(N / E))
         int il = i;
         if constexpr (ROWMAP) il = (g.map_load && !zero) ? g.rows(i) : i;
         x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)il * g.es, i, col, outer);
+    }
+    if (g.l2pf > 0) {
+        // tile of the CTA g.l2pf launches ahead (x fastest, then y)
+        const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + g.l2pf;
+        const int by = (int)(lin / gridDim.x), bx = (int)(lin - (long long)by * gridDim.x);
+        if (by < (int)gridDim.y) {
+            const int pfield = bx % g.nf;
+            const int pcol = (bx / g.nf) * TK + c;
+            const int poidx = by + g.outer0;
+            const int pouter = poidx < g.outer_lo ? poidx : poidx + g.outer_gap;
+            const long long pbase = (long long)pouter * g.os + pcol;
+            // one request per 128-byte line: lanes c with (c * 16) % 128 == 0
+            if (pcol < g.ncols && (c % (TK < 8 ? TK : 8)) == 0) {
+#pragma unroll
+                for (int m = 0; m < E; ++m) {
+                    const int i = t + m * T;
+                    if (!(g.skip_load && i >= g.band_lo && i < g.band_hi)) {
+                        int il = i;
+                        if constexpr (ROWMAP) il = g.map_load ? g.rows(i) : i;
+                        ld.prefetch(pfield, pbase + (long long)il * g.es, i, pcol, pouter);
+                    }
+                }
+            }
+        }
     }
     fft_line<N, E, DIR, TK, 1>(x, plane, t, c, tw, SyncBlock());
     if (active) {

@@ -1,8 +1,10 @@
 // Strided-axis (y / z) FFT passes and the fused first inverse pass (curl / ns2d prologue on load).
 #include "internal.h"
 #include <stdlib.h>
+#include <string.h>
 
 #include "passes.cuh"
+#include "strided_tma.cuh"
 
 // per-size configuration of the strided pass: E points per thread, TK columns per CTA tile
 template <int N> struct SCfg;
@@ -38,6 +40,10 @@ static int launch_strided_cfg(Geom g, int nf, L ld, S st, const cplx* tw, cudaSt
     }
     g.nf = nf;
     dim3 grid(((g.ncols + TK - 1) / TK) * nf, g.nouter, 1);
+    // L2 prefetch distance (CTAs ahead); development knob B2_L2PF, default: about half a wave of
+    // resident CTAs for the long lines (measured best, profiles/r2_tuning.md), off for the short ones (tiles small, many CTAs per SM)
+    static const int l2pf_env = getenv("B2_L2PF") ? atoi(getenv("B2_L2PF")) : -1;
+    g.l2pf = l2pf_env >= 0 ? l2pf_env : (N >= 1024 ? 150 : 0);
     kern<<<grid, TK*(N / E), smem, s>>>(g, ld, st, tw);
     B2_LAUNCH_CHECK("fft_strided_kernel");
     return 0;
@@ -78,7 +84,112 @@ struct LoadFromIn {
     B2_DEVINL cplx operator()(int f, long long off, int i, int col, int outer) const {
         return in.xf(f, *in.ptr(f, off, i, col, outer), i, col, outer);
     }
+    B2_DEVINL void prefetch(int f, long long off, int i, int col, int outer) const {
+        b2_prefetch_l2(in.ptr(f, off, i, col, outer));
+    }
 };
+
+// ------------------------------------------------------------------------------- TMA-pipelined path
+typedef CUresult (*b2_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                       CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                       CUtensorMapFloatOOBfill);
+static b2_encode_tiled_fn encode_tiled() {
+    static b2_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (b2_encode_tiled_fn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+static int strided_tma_mode() {  // development knob: B2_STMA=0 disables the TMA-pipelined kernels
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B2_STMA");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+template <class In> struct TmaSource { static constexpr bool ok = false; };
+template <> struct TmaSource<PlainIn> {
+    static constexpr bool ok = true;
+    static const cplx* base(const PlainIn& in, int f) { return in.in[f]; }
+};
+
+// returns 1 if the pass was launched, 0 if this path does not apply (caller falls back), < 0 on error
+template <int N, int E, int TK, int DIR, bool TMA, class In, class S>
+static int try_launch_strided_tma(Geom g, int nf, const In& in, S st, const cplx* tw, cudaStream_t s) {
+    if (g.dim_nk == 0 || g.cs != 1 || g.map_load || g.map_store) return 0;
+    b2_encode_tiled_fn enc = TMA ? encode_tiled() : nullptr;
+    if (TMA && !enc) return 0;
+    TmaGeom tg;
+    const long long plane_stride = (long long)g.dim_n1 * g.dim_nk;
+    if (g.es == g.dim_nk && g.os == plane_stride) tg.axis_mid = 1;
+    else if (g.es == plane_stride && g.os == g.dim_nk) tg.axis_mid = 0;
+    else return 0;
+    const int lo_rows = g.skip_load ? g.band_lo : N;
+    const int up_rows = g.skip_load ? N - g.band_hi : 0;
+    const int maxr = lo_rows > up_rows ? lo_rows : up_rows;
+    if (maxr <= 0) return 0;
+    const int nb = (maxr + 255) / 256;
+    tg.rb = (maxr + nb - 1) / nb;
+    constexpr int RALIGN = TK * (int)sizeof(cplx) >= 128 ? 1 : 128 / (TK * (int)sizeof(cplx));
+    tg.rb = (tg.rb + RALIGN - 1) / RALIGN * RALIGN;  // every box lands on a 128-byte boundary
+    if (tg.rb > 256) return 0;
+    if (!TMA) tg.rb = 1;  // cp.async: the buffer holds exactly the kept rows
+    tg.nbl = (lo_rows + tg.rb - 1) / tg.rb;
+    tg.nbu = up_rows > 0 ? (up_rows + tg.rb - 1) / tg.rb : 0;
+    tg.up_row0 = g.skip_load ? g.band_hi : N;
+    tg.pb_rows = (tg.nbl + tg.nbu) * tg.rb;
+    tg.nct = (g.ncols + TK - 1) / TK;
+    const long long ntiles = (long long)tg.nct * g.nouter * nf;
+    if (ntiles <= 0 || ntiles > 0x7fffffffLL) return 0;
+    tg.ntiles = (int)ntiles;
+    const size_t smem = ((size_t)N * TK + (size_t)tg.pb_rows * TK) * sizeof(cplx) + 16;
+    if (smem > 227 * 1024) return 0;
+    TmaSet maps;
+    const cuuint64_t gdim[3] = {(cuuint64_t)2 * g.dim_nk, (cuuint64_t)g.dim_n1, (cuuint64_t)g.dim_n0};
+    const cuuint64_t gstr[2] = {(cuuint64_t)g.dim_nk * sizeof(cplx), (cuuint64_t)plane_stride * sizeof(cplx)};
+    const cuuint32_t box_mid[3] = {2 * TK, (cuuint32_t)tg.rb, 1}, box_out[3] = {2 * TK, 1, (cuuint32_t)tg.rb};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    static const int l2p = getenv("B2_STMA_L2") ? atoi(getenv("B2_STMA_L2")) : 1;
+    PfSources srcs;
+    for (int f = 0; f < B2_MAXF; ++f) srcs.src[f] = TmaSource<In>::base(in, f < nf ? f : 0);
+    for (int f = 0; TMA && f < nf; ++f) {
+        const cplx* base = TmaSource<In>::base(in, f);
+        if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return 0;
+        CUresult r = enc(&maps.m[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, gdim, gstr,
+                         tg.axis_mid ? box_mid : box_out, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE,
+                         l2p == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                  : (l2p == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return 0;
+    }
+    for (int f = nf; TMA && f < B2_MAXF; ++f) maps.m[f] = maps.m[0];
+    if (!TMA) memset(&maps, 0, sizeof(maps));
+    auto kern = fft_strided_tma_kernel<N, E, TK, DIR, TMA, In, S>;
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return b2i_set_error("fft_strided_tma_kernel: %s", cudaGetErrorString(ce));
+    int dev = 0, nsm = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TK * (N / E), smem);
+    if (occ < 1) return 0;
+    long long grid = (long long)nsm * occ;
+    if (grid > ntiles) grid = ntiles;
+    g.nf = nf;
+    kern<<<(unsigned)grid, TK*(N / E), smem, s>>>(maps, srcs, g, tg, in, st, tw);
+    B2_LAUNCH_CHECK("fft_strided_tma_kernel");
+    return 1;
+}
 
 template <int N, int DIR, bool ROWMAP, class L, class S>
 static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStream_t s) {
@@ -106,6 +217,27 @@ static int launch_strided_n(Geom g, int nf, L ld, S st, const cplx* tw, cudaStre
 template <int DIR, bool ROWMAP = false, class In, class S>
 static int launch_strided(bool fast, int N, Geom g, int nf, In in, S st, const cplx* tw, cudaStream_t s) {
     LoadFromIn<In> ld{in};
+    if constexpr (!ROWMAP && TmaSource<In>::ok) {
+        if (fast && (N == 512 || N == 1024 || N == 2048)) {
+            // development knob B2_STMA: 0 LDG kernels, 1 TMA tensor-map prefetch (TK 4 / B2_STMA_TK=8),
+            // 2 cp.async prefetch (TK 4)
+            int r = 0;
+            const int mode = strided_tma_mode();
+            static const int tk8 = getenv("B2_STMA_TK") ? atoi(getenv("B2_STMA_TK")) == 8 : 0;
+            if (mode == 1) {
+                if (N == 512) r = tk8 ? try_launch_strided_tma<512, 16, 8, DIR, true>(g, nf, in, st, tw, s)
+                                      : try_launch_strided_tma<512, 16, 4, DIR, true>(g, nf, in, st, tw, s);
+                else if (N == 1024) r = tk8 ? try_launch_strided_tma<1024, 16, 8, DIR, true>(g, nf, in, st, tw, s)
+                                            : try_launch_strided_tma<1024, 16, 4, DIR, true>(g, nf, in, st, tw, s);
+                else r = try_launch_strided_tma<2048, 16, 4, DIR, true>(g, nf, in, st, tw, s);
+            } else if (mode == 2) {
+                if (N == 512) r = try_launch_strided_tma<512, 16, 4, DIR, false>(g, nf, in, st, tw, s);
+                else if (N == 1024) r = try_launch_strided_tma<1024, 16, 4, DIR, false>(g, nf, in, st, tw, s);
+                else r = try_launch_strided_tma<2048, 16, 4, DIR, false>(g, nf, in, st, tw, s);
+            }
+            if (r != 0) return r < 0 ? r : 0;
+        }
+    }
     if (fast) {
         switch (N) {
 #define B2_CASE(n) case n: return launch_strided_n<n, DIR, ROWMAP>(g, nf, ld, st, tw, s);
@@ -140,6 +272,7 @@ static Geom geom_pruned(const b2_plan* p, int axis, int dir) {
     }
     g.skip_load = dir > 0;
     g.skip_store = dir < 0;
+    g.dim_nk = p->nk; g.dim_n1 = p->n1; g.dim_n0 = p->n0;
     return g;
 }
 
@@ -158,6 +291,7 @@ static Geom geom_for_axis(const b2_plan* p, int axis) {
     }
     g.cs = 1;
     g.nf = 1;
+    g.dim_nk = p->nk; g.dim_n1 = p->n1; g.dim_n0 = p->n0;
     return g;
 }
 
@@ -209,6 +343,11 @@ struct Ns2dIn {
         }
         return make_double2(-cf * r.y, cf * r.x);
     }
+};
+
+template <> struct TmaSource<Ns2dIn> {
+    static constexpr bool ok = true;
+    static const cplx* base(const Ns2dIn& in, int) { return in.rot; }
 };
 
 // ns3d / strat: in[] = nvar stage-input fields (v, [b]); the vorticity has already been written to
@@ -280,6 +419,7 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     g.es = p->nk;
     g.os = (long long)p->n1 * p->nk;
     g.nf = nf;
+    g.dim_nk = p->nk; g.dim_n1 = p->n1; g.dim_n0 = p->n0;
     SlabMapper map;
     map.nzl = p->nzl;
     map.zc = p->nzl / p->slab_nc;
