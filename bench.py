@@ -68,7 +68,10 @@ def parse_args():
     ap.add_argument("--scheme", default="RK4", choices=["RK4", "RK2"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-n", type=int, default=128, help="grid size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=256, help="grid size of the bounded CPU sample")
+    ap.add_argument("--allow-shrink", action="store_true",
+                    help="halve the grid instead of failing when it does not fit device memory")
+    ap.add_argument("--no-parity", action="store_true", help="skip the golden parity check before the timed region")
     return ap.parse_args()
 
 
@@ -175,7 +178,7 @@ def reference_arm(args):
     if rank != 0:
         return
     n = args.cpu_n
-    r = cpu_run(args.solver, args.scheme, n, args.steps, min(args.warmup, 1), max_seconds=150.0)
+    r = cpu_run(args.solver, args.scheme, n, args.steps, args.warmup, max_seconds=200.0)
     sample = (f"{args.solver} {n}^{3 if args.solver != 'ns2d' else 2} {args.scheme} noise init, {r['steps']} steps "
               f"(bounded sample of the {args.n}^3 workload; value is per grid point so sizes compare)")
     line = {
@@ -185,7 +188,7 @@ def reference_arm(args):
         "unit": UNIT,
         "n_gpus": args.gpus,
         "steps": r["steps"],
-        "warmup": min(args.warmup, 1),
+        "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"],
         "higher_is_better": True,
         "scaling": "strong",
@@ -224,6 +227,7 @@ def make_sim(args, torch):
     sim = cls(p, fused=True)
     sim.time_stepping.check_nan_period = 0  # checked once after the timed region
     init_noise_on_device(sim, torch)
+    torch.cuda.empty_cache()  # the init temporaries (one physical field) go back before the step buffers come
     return sim
 
 
@@ -239,6 +243,7 @@ def init_noise_on_device(sim, torch, seed=42):
     for i in range(nvar):
         x.uniform_(-0.5, 0.5, generator=g)
         oper.fft_as_arg(x, S[i])
+    del x
     S[(slice(None),) + (0,) * sim.ndim] = 0.0
     if sim.ndim == 3:
         oper.project_perpk3d(S[0], S[1], S[2])
@@ -274,7 +279,7 @@ def make_slab_sim(args, torch, dist):
     p.time_stepping.USE_CFL = False
     p.time_stepping.deltat0 = 1e-4
     p.time_stepping.type_time_scheme = args.scheme
-    sim = SlabSimul(args.solver, p)
+    sim = SlabSimul(args.solver, p, lean=True)
     dev = sim.device
     dk = 2 * math.pi / (2 * math.pi)
     kadim = lambda m: torch.fft.fftfreq(m, 1.0 / m, dtype=torch.float64, device=dev).abs()
@@ -304,6 +309,74 @@ def make_slab_sim(args, torch, dist):
     return sim
 
 
+def parity_check(args, torch, world, rank):
+    """Step committed reference goldens (tests/golden/*.npz, produced by the reference's own code)
+    through the SAME plan type the timed region uses (fused single-GPU plan, or the slab plan on all
+    ranks) and return the max relative state error.  Puts parity evidence into the bench line of
+    every N (the GPU test suite skips the multi-GPU cases on a single-GPU box)."""
+    import numpy as np
+
+    gdir = os.path.join(ROOT, "tests", "golden")
+    names = {"ns3d": ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f"], "ns3d.strat": ["strat_16x16x16_rk4"],
+             "ns2d": ["ns2d_32x32_rk4"]}[args.solver]
+    worst, cases = 0.0, []
+    for name in names:
+        path = os.path.join(gdir, name + ".npz")
+        if not os.path.exists(path):
+            continue
+        z = np.load(path)
+        meta = json.loads(str(z["meta"]))
+        kw = dict(meta["params"])
+        shape = meta["shape"]
+        if world > 1:
+            from fluidsim_b200.params import create_default_params
+            from fluidsim_b200.slab import SlabSimul
+
+            if shape[2] % world or shape[1] % world:
+                continue
+            p = create_default_params(meta["solver"])
+            p.oper.nx, p.oper.ny, p.oper.nz = shape
+        else:
+            from fluidsim_b200.solvers import SIMUL_CLASSES
+
+            p = SIMUL_CLASSES[meta["solver"]].create_default_params()
+            p.oper.nx, p.oper.ny = shape[0], shape[1]
+            if len(shape) == 3:
+                p.oper.nz = shape[2]
+        for key in ("Lx", "Ly", "Lz", "coef_dealiasing", "truncation_shape"):
+            if key in kw:
+                setattr(p.oper, key, kw.pop(key))
+        p.time_stepping.USE_CFL = False
+        p.time_stepping.type_time_scheme = kw.pop("type_time_scheme", "RK4")
+        p.time_stepping.deltat0 = kw.pop("deltat0", 1e-2)
+        for key in list(kw):
+            setattr(p, key, kw.pop(key))
+        if world > 1:
+            sim = SlabSimul(meta["solver"], p, lean=True)
+            sim.set_mask_from_global(z["mask"])
+            sim.set_state_from_global(z["state0"])
+            for _ in range(meta["nsteps"]):
+                sim.one_time_step()
+            got = sim.gather_state()
+        else:
+            sim = SIMUL_CLASSES[meta["solver"]](p, fused=True)
+            sim.oper.where_dealiased = torch.from_numpy(np.ascontiguousarray(z["mask"])).to(sim.oper.device)
+            sim.state.state_spect.tensor.copy_(torch.from_numpy(np.ascontiguousarray(z["state0"])))
+            sim.state.mark_spect_modified()
+            for _ in range(meta["nsteps"]):
+                sim.time_stepping.one_time_step()
+            got = sim.state.state_spect.numpy()
+        ref = z["stateN"]
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        worst = max(worst, err)
+        cases.append(f"{name} x{meta['nsteps']} steps")
+        del sim
+    torch.cuda.synchronize()
+    return {"max_rel_err": worst, "cases": cases, "tolerance": 1e-10,
+            "against": "reference goldens (tests/golden, generated by the reference's own modules)",
+            "plan": "slab x%d (lean buffers)" % world if world > 1 else "single-GPU fused"}
+
+
 def own_arm(args):
     import torch
     import torch.distributed as dist
@@ -322,18 +395,24 @@ def own_arm(args):
     from fluidsim_b200 import _lib
 
     hbm_peak, peak_src = peaks()
-    # memory guard (single GPU): the fused path holds 15 (ns3d) / 19 (strat) K fields; fall back to
-    # the next smaller power of two rather than drive the box out of memory
+    # memory guard (single GPU): the fused path holds 12 (ns3d, aliased buffers) / 19 (strat) K fields
+    # plus the mask; a grid that does not fit is an ERROR for the headline (no silent halving)
     size_note = None
     if args.solver != "ns2d" and world == 1:  # (slab runs split the same grid: less memory per GPU)
         free_b, _total_b = torch.cuda.mem_get_info()
-        nfields = {"ns3d": 15, "ns3d.strat": 19}[args.solver]
+        nfields = {"ns3d": 12, "ns3d.strat": 19}[args.solver]
         while args.n > 64:
-            need = (nfields + 1.5) * 16.0 * args.n * args.n * (args.n // 2 + 1)
-            if need < 0.92 * free_b:
+            need = (nfields + 0.2) * 16.0 * args.n * args.n * (args.n // 2 + 1)
+            if need < free_b:
                 break
-            size_note = f"requested grid did not fit {free_b / 1e9:.0f} GB of free device memory; halved"
+            msg = (f"{args.solver} {args.n}^3 needs {need / 1e9:.0f} GB of device memory, {free_b / 1e9:.0f} GB free")
+            if not args.allow_shrink:
+                raise RuntimeError(msg + " (use --allow-shrink to halve the grid, or more GPUs)")
+            size_note = msg + "; halved"
             args.n //= 2
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(args, torch, world, rank)
     if world > 1:
         sim = make_slab_sim(args, torch, dist)
         ts = sim
@@ -411,54 +490,81 @@ def own_arm(args):
         passes = class_passes(args.solver, *kept)
         tot = sum(msarr)
         best = None
+        nst = 4 if args.scheme == "RK4" else 2
         for i, name in enumerate(CLASS_NAMES):
             if cnt[i] == 0:
                 continue
-            avg = msarr[i] / cnt[i]
-            ach = passes[i] * F / (avg * 1e-3) / 1e9
-            classes[name] = {"launches_per_step": cnt[i] / nprof, "avg_ms": avg, "share": msarr[i] / tot,
-                             "alg_GBps": ach, "frac": ach / hbm_peak}
+            # class_passes are per launch of the SINGLE-GPU structure (one launch per stage and class,
+            # nst + 1 for the epilogue class with its stage-0 curl kernel); the slab path issues the
+            # same work as several per-field / per-chunk launches, so rates are formed per STEP
+            per_step_launches_1gpu = (nst + 1) if (i == 5 and args.solver != "ns2d") else nst
+            bytes_step = passes[i] * F * per_step_launches_1gpu
+            ms_step = msarr[i] / nprof
+            ach = bytes_step / (ms_step * 1e-3) / 1e9
+            classes[name] = {"launches_per_step": cnt[i] / nprof, "avg_ms": msarr[i] / cnt[i],
+                             "ms_per_step": ms_step, "share": msarr[i] / tot,
+                             "alg_bytes_per_step": bytes_step, "alg_GBps": ach, "frac": ach / hbm_peak}
             if best is None or msarr[i] > msarr[best]:
                 best = i
         bname = CLASS_NAMES[best]
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture of this
-        # configuration (profiles/r1_ncu_xpass_1024_raw.csv: dram read 35.14 GB + write 17.23 GB)
-        traffic = 52.37e9 if (bname == "x_fused_c2r_cross_r2c" and args.n == 1024 and world == 1
-                              and args.solver == "ns3d") else None
+        # DRAM traffic of the dominant kernel: read from the committed summary of the `ncu --set full`
+        # capture of this configuration (profiles/r2_ncu_traffic.json), never a literal
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) as f:
+                tj = json.load(f)
+            key = f"{args.solver}:{args.n}:{world}:{bname}"
+            if key in tj:
+                traffic = tj[key]["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
+        lps = classes[bname]["launches_per_step"]
         roofline = {"bound": "hbm", "kernel": bname, "achieved": classes[bname]["alg_GBps"], "peak": hbm_peak,
                     "unit": "GB/s", "frac": classes[bname]["frac"], "traffic": traffic,
                     "peak_source": peak_src,
-                    "alg_bytes_per_launch": passes[best] * F,
+                    "alg_bytes_per_launch": classes[bname]["alg_bytes_per_step"] / lps,
+                    "avg_launch_ms": classes[bname]["avg_ms"],
                     "note": "algorithmic bytes of the launch as built (dealias-pruned: kept kx fraction "
-                            f"{kept[0]:.3f}, ky {kept[1]:.3f}, kz {kept[2]:.3f})"}
+                            f"{kept[0]:.3f}, ky {kept[1]:.3f}, kz {kept[2]:.3f}); per-GPU figures (rank 0)"}
     barrier()
 
     # ---- end to end through the public API with HOST buffers (state in pinned host memory)
     e2e = None
     e2e_note = None
-    if not args.no_e2e and world == 1 and host_mem_available() < 3 * S.numel() * 16:
+    if not args.no_e2e and host_mem_available() < 3 * S.numel() * 16 * (world if world > 1 else 1):
         e2e_note = "skipped: not enough host memory for a pinned copy of the state"
-    elif not args.no_e2e and world == 1:
+    elif not args.no_e2e:
+        # every rank keeps ITS part of the state in pinned host memory and copies it in and out around
+        # every step (the reference-facing call with host buffers); max over ranks
         host = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
         host.copy_(S)
-        torch.cuda.synchronize()
         ksteps = max(2, min(args.steps, 5))
+        barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
             S.copy_(host, non_blocking=True)
-            sim.state.mark_spect_modified()  # host data: the stepper re-checks that it is dealiased
+            if world == 1:
+                sim.state.mark_spect_modified()  # host data: the stepper re-checks that it is dealiased
+            else:
+                sim.mark_spect_modified()
             ts.one_time_step()
             host.copy_(S, non_blocking=True)
             torch.cuda.synchronize()
+        barrier()
         dt = (time.perf_counter() - t0) / ksteps
-        nbytes = S.numel() * 16
+        if world > 1:
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        nbytes = S.numel() * 16 * world
         e2e = {"value": npts / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "steps": ksteps}
+               "ms_per_step": dt * 1e3, "steps": ksteps,
+               "note": "whole-job bytes (all ranks); each rank copies its slab over its own PCIe link"}
         del host
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_run(args.solver, args.scheme, args.cpu_n, 10, 1, max_seconds=20.0)
+        r = cpu_run(args.solver, args.scheme, args.cpu_n, 3, 1, max_seconds=25.0)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                         "sample": f"{args.solver} {r['n']}^{ndim} {args.scheme}, {r['steps']} steps of the numpy/"
                                   f"pocketfft oracle port, {r['ms_per_step']:.0f} ms/step"}
@@ -479,10 +585,14 @@ def own_arm(args):
         nfft = {"ns3d": 36, "ns3d.strat": 52}.get(args.solver, 0) if args.scheme == "RK4" else 0
         nvlink = None
         if world > 1:
-            nvl_bytes = nfft * F * (world - 1) / world  # sent per GPU per direction per step
-            nvlink = {"bytes_per_gpu_per_step": nvl_bytes, "peak_GBps": 770.0,
+            # bytes sent per GPU, per direction, per step: every 3-D FFT moves (P-1)/P of the local
+            # field once; the pruned exchange carries only kept ky rows x kx < keepx columns
+            nvl_full = nfft * F * (world - 1) / world
+            nvl_bytes = nvl_full * kept[0] * kept[1]
+            nvlink = {"bytes_per_gpu_per_step": nvl_bytes, "bytes_unpruned": nvl_full, "peak_GBps": 770.0,
                       "peak_source": "measured peer copy per direction (B200_PROFILING.md)",
-                      "floor_ms": nvl_bytes / 770e9 * 1e3}
+                      "floor_ms": nvl_bytes / 770e9 * 1e3,
+                      "frac_of_step": nvl_bytes / 770e9 * 1e3 / ms_per_step}
         line = {
             "metric": METRIC if args.solver == "ns3d" else f"{args.solver}_{args.scheme.lower()}_grid_points_steps_per_s",
             "value": value,
@@ -504,7 +614,7 @@ def own_arm(args):
                 "size_note": size_note,
                 "state_bytes_per_gpu": S.numel() * 16,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
-                "parallelism": "single GPU" if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all)",
+                "parallelism": "single GPU" if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all; lean buffers)",
             },
             "nvlink": nvlink,
             "roofline": roofline,
@@ -521,6 +631,7 @@ def own_arm(args):
             "e2e": e2e if e2e is not None else ({"note": e2e_note} if e2e_note else None),
             "gpu_launches": launches,
             "clocks": clocks,
+            "parity_check": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,6 +72,10 @@ SIGNATURES = {
     "b2_plan_create_slab": [C.POINTER(_p), _i, _i, _i, _d, _d, _d, _i, _i, _i],
     "b2_slab_kept_rows": [_p, C.POINTER(_i)],
     "b2_slab_set_buffers": [_p, _p, _p],
+    "b2_slab_set_buffer_strides": [_p, _ll, _ll],
+    "b2_slab_buffer_need": [_p, C.POINTER(_ll), C.POINTER(_ll)],
+    "b2_set_aliasing": [_p, _i],
+    "b2_set_forcing_sparse": [_p, _ll, _p, _p, _i],
     "b2_slab_set_pruning": [_p, _i, _i, _i, _i, _i, _i, _i, _i],
     "b2_slab_curl": [_p, _p, _p],
     "b2_slab_zinv": [_p, _p, _i, _i, _p],

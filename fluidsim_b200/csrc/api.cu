@@ -956,7 +956,6 @@ extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, do
 }
 
 extern "C" int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar) {
-    (void)p;
     switch (solver) {
         case B2_SOLVER_NS3D: *nwork = 6; *nvar = 3; return 0;
         case B2_SOLVER_NS3D_STRAT: *nwork = 7; *nvar = 4; return 0;
@@ -975,8 +974,8 @@ enum { M_TEND = 0, M_RK4_0, M_RK4_1, M_RK4_2, M_RK4_3, M_RK2_0, M_RK2_1 };
 struct RKArgs {
     KGrid g;
     Visc visc;
-    cplx* W;          // raw FFT output: nwork_out fields, stride fsize; W[3..5] receive the
-                      // vorticity of the next stage input
+    cplx* W;          // raw FFT output: nout fields, stride fsize
+    cplx* Wo;         // 3 fields: receive the vorticity of the next stage input
     const cplx* Sin;  // stage input (strat coupling terms)
     double fcor;      // Coriolis parameter added to omega_z(k=0) (0 if params.f is None)
     cplx* S;          // state (nvar fields)
@@ -1081,9 +1080,9 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
                 cplx ox, oy, oz;
                 curl3(Kx, Ky, Kz, Sn[0], Sn[1], Sn[2], ox, oy, oz);
                 if (origin) oz.x += a.fcor;
-                a.W[3 * a.fsize + i] = ox;
-                a.W[4 * a.fsize + i] = oy;
-                a.W[5 * a.fsize + i] = oz;
+                a.Wo[i] = ox;
+                a.Wo[a.fsize + i] = oy;
+                a.Wo[2 * a.fsize + i] = oz;
             }
         }
         if (MODE == M_RK4_3 || MODE == M_RK2_1) {
@@ -1109,10 +1108,47 @@ static int launch_rk_stage_s(int mode, const RKArgs& a, unsigned grid, cudaStrea
     return 0;
 }
 
+// tendencies_fft += forcing_fft (/root/reference/fluidsim/solvers/ns3d/solver.py:243-244,
+// ns2d/solver.py:185-186): the forcing of fluidsim's forcing makers lives on a few low-wavenumber
+// modes ((2 nkmax_forcing)^3 at most, base/forcing/specific.py:137-345), so it is kept as a sparse
+// list and added to the raw transform output in front of the epilogue -- no field-sized pass.
+__global__ void forcing_add_kernel(cplx* W, long long fsize, int nvar, long long nm, const long long* idx,
+                                   const cplx* val) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nm * nvar) return;
+    const int v = (int)(j / nm);
+    const long long m = j - (long long)v * nm;
+    const cplx f = val[j];
+    cplx* dst = W + (long long)v * fsize + idx[m];
+    dst->x += f.x;
+    dst->y += f.y;
+}
+
+extern "C" int b2_set_forcing_sparse(b2_plan* p, long long nmodes, const long long* idx, const double* val,
+                                     int nvar) {
+    if (nmodes < 0) return b2i_set_error("b2_set_forcing_sparse: negative mode count");
+    if (nmodes > 0 && (!idx || !val)) return b2i_set_error("b2_set_forcing_sparse: NULL arrays");
+    const int nv_max = p->solver == B2_SOLVER_NS2D ? 1 : 3;
+    if (nmodes > 0 && (nvar < 1 || nvar > nv_max))
+        return b2i_set_error("b2_set_forcing_sparse: nvar = %d (the forced variables are the %d leading state "
+                             "variables; a forced buoyancy is not supported)", nvar, nv_max);
+    p->force_n = nmodes;
+    p->force_idx = idx;
+    p->force_val = (const cplx*)val;
+    p->force_nvar = nvar;
+    return 0;
+}
+
 static int launch_rk_stage(b2_plan* p, int mode, const RKArgs& a, cudaStream_t s) {
     ProfScope ps(PC_RK, s);
     const unsigned grid = nrows_fused(p);
     if (grid == 0) return 0;
+    if (p->force_n > 0) {
+        const long long tot = p->force_n * p->force_nvar;
+        forcing_add_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, s>>>(a.W, a.fsize, p->force_nvar, p->force_n,
+                                                                        p->force_idx, p->force_val);
+        B2_LAUNCH_CHECK("forcing_add_kernel");
+    }
     switch (p->solver) {
         case B2_SOLVER_NS3D: return launch_rk_stage_s<B2_SOLVER_NS3D>(mode, a, grid, s);
         case B2_SOLVER_NS3D_STRAT: return launch_rk_stage_s<B2_SOLVER_NS3D_STRAT>(mode, a, grid, s);
@@ -1159,7 +1195,7 @@ static int nonlinear_raw(b2_plan* p, const cplx* Sin, bool need_curl, cudaStream
     cplx* W[8];
     const cplx* Wc[8];
     for (int v = 0; v < nvar; ++v) in[v] = Sin + v * fs;
-    for (int f = 0; f < nwork; ++f) Wc[f] = W[f] = p->work + f * fs;
+    for (int f = 0; f < nwork; ++f) Wc[f] = W[f] = p->wfield(f);
     const int nout = p->solver == B2_SOLVER_NS3D ? 3 : (p->solver == B2_SOLVER_NS3D_STRAT ? 6 : 1);
     const double scale = 1.0 / ((double)p->n0 * p->n1 * p->n2);
     int e;
@@ -1238,6 +1274,7 @@ static int check_fused_ready(b2_plan* p, bool need_rk) {
                              p->n1, p->n2);
     if (!p->work) return b2i_set_error("b2_set_buffers has not been called (work)");
     if (need_rk && (!p->acc || !p->stage)) return b2i_set_error("b2_set_buffers: acc/stage missing");
+    if (p->alias_tw && !p->stage) return b2i_set_error("aliased buffers need the stage buffer");
     return 0;
 }
 
@@ -1245,7 +1282,8 @@ static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     RKArgs a;
     a.g = kgrid_fused(p);
     a.visc = visc_of(p, p->nu2, p->nu4, p->nu8, p->num4);
-    a.W = p->work;
+    a.W = p->wfield(0);
+    a.Wo = p->wfield(3);
     a.Sin = Sin;
     a.S = S;
     a.A = p->acc;
@@ -1368,12 +1406,47 @@ extern "C" int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb) {
     return 0;
 }
 
+// elements between consecutive fields of xa / xb (default: a full K field).  With the pruned
+// exchange a field needs only ny * nz_loc * keepx elements in xa and (kept ky rows) * nz_loc * keepx
+// in xb: b2_slab_buffer_need reports both for the current pruning state.
+extern "C" int b2_slab_set_buffer_strides(b2_plan* p, long long xa_field, long long xb_field) {
+    if (!p->slab) return b2i_set_error("b2_slab_set_buffer_strides: not a slab plan");
+    if (xa_field < 0 || xb_field < 0) return b2i_set_error("b2_slab_set_buffer_strides: negative stride");
+    p->xa_fs = xa_field;
+    p->xb_fs = xb_field;
+    return 0;
+}
+extern "C" int b2_slab_buffer_need(const b2_plan* p, long long* xa_field, long long* xb_field) {
+    if (!p->slab) return b2i_set_error("b2_slab_buffer_need: not a slab plan");
+    if (p->prune) {
+        const long long nyk = p->gy - (p->gyk_hi - p->gyk_lo);
+        *xa_field = (long long)p->gy * p->nzl * p->keepx;
+        *xb_field = nyk * p->nzl * p->keepx;
+    } else {
+        *xa_field = *xb_field = p->fsize();
+    }
+    return 0;
+}
+// ns3d only: raw transform outputs are written into `stage` and rewritten in place by the epilogue;
+// `work` then holds only the 3 vorticity fields (12 instead of 15 K fields on one GPU)
+extern "C" int b2_set_aliasing(b2_plan* p, int on) {
+    if (on && p->solver != B2_SOLVER_NS3D) return b2i_set_error("b2_set_aliasing: ns3d only (set the physics first)");
+    p->alias_tw = on ? 1 : 0;
+    return 0;
+}
+
 static int slab_ready(b2_plan* p) {
     if (!p->slab) return b2i_set_error("not a slab plan");
     if (p->solver != B2_SOLVER_NS3D && p->solver != B2_SOLVER_NS3D_STRAT)
         return b2i_set_error("slab stepping supports ns3d and ns3d.strat");
     if (!b2_plan_is_fast(p)) return b2i_set_error("slab stepping needs power-of-two sizes in [8, 2048]");
     if (!p->work || !p->xa || !p->xb) return b2i_set_error("slab buffers not set");
+    if (p->alias_tw && !p->stage) return b2i_set_error("aliased buffers need the stage buffer");
+    long long na, nb;
+    b2_slab_buffer_need(p, &na, &nb);
+    if (p->xa_stride() < na || p->xb_stride() < nb)
+        return b2i_set_error("slab exchange buffers too small for this pruning state (need %lld / %lld elements "
+                             "per field, have %lld / %lld)", na, nb, p->xa_stride(), p->xb_stride());
     return 0;
 }
 
@@ -1388,7 +1461,7 @@ extern "C" int b2_slab_curl(b2_plan* p, const double* S_in, void* stream) {
     if (nrows_fused(p) == 0) return 0;
     ProfScope ps(PC_RK, s);
     rot_kernel<<<nrows_fused(p), B2_ROW_THREADS, 0, s>>>(kgrid_fused(p), Sin, Sin + fs, Sin + 2 * fs,
-                                                        p->work + 3 * fs, p->work + 4 * fs, p->work + 5 * fs,
+                                                        p->wfield(3), p->wfield(4), p->wfield(5),
                                                         p->has_f ? p->f : 0.0);
     B2_LAUNCH_CHECK("rot_kernel");
     return 0;
@@ -1413,8 +1486,8 @@ extern "C" int b2_slab_zinv(b2_plan* p, const double* S_in, int f0, int f1, void
     const cplx* in[8];
     cplx* out[8];
     for (int f = f0; f < f1; ++f) {
-        in[f - f0] = f < 3 ? Sin + f * fs : (f < 6 ? p->work + f * fs : Sin + 3 * fs);
-        out[f - f0] = p->xa + f * fs;
+        in[f - f0] = f < 3 ? Sin + f * fs : (f < 6 ? p->wfield(f) : Sin + 3 * fs);
+        out[f - f0] = p->xa + f * p->xa_stride();
     }
     ProfScope ps(PC_FIRST_INV, s);
     return b2i_slab_zpass(p, +1, in, out, f1 - f0, s);
@@ -1440,8 +1513,8 @@ extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, int chunk, void* stream)
     const cplx* in[8];
     cplx* out[8];
     for (int f = f0; f < f1; ++f) {
-        in[f - f0] = p->xb + f * fs;
-        out[f - f0] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+        in[f - f0] = p->xb + f * p->xb_stride();
+        out[f - f0] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
     }
     ProfScope ps(PC_Y_INV, s);
     for (int c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? p->slab_nc : chunk + 1); ++c)
@@ -1457,7 +1530,7 @@ extern "C" int b2_slab_xpass(b2_plan* p, int chunk, void* stream) {
     if (chunk >= p->slab_nc) return b2i_set_error("b2_slab_xpass: bad chunk");
     const long long fs = p->fsize();
     cplx* XW[8];
-    for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * fs : p->xb + f * fs;
+    for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
     const int pitch = p->prune ? p->keepx : p->nk;
     const long long lines_c = (long long)p->gy * (p->nzl / p->slab_nc);
@@ -1478,8 +1551,8 @@ extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, int chunk, void* stream)
     const cplx* in[8];
     cplx* out[8];
     for (int f = f0; f < f1; ++f) {
-        in[f - f0] = p->prune ? p->xa + f * fs : p->xb + f * fs;
-        out[f - f0] = p->xb + f * fs;
+        in[f - f0] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+        out[f - f0] = p->xb + f * p->xb_stride();
     }
     ProfScope ps(PC_Y_FWD, s);
     for (int c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? p->slab_nc : chunk + 1); ++c)
@@ -1497,7 +1570,7 @@ extern "C" int b2_slab_zfwd(b2_plan* p, int f0, int f1, void* stream) {
     const long long fs = p->fsize();
     const cplx* in[8];
     cplx* out[8];
-    for (int f = f0; f < f1; ++f) { in[f - f0] = p->xa + f * fs; out[f - f0] = p->work + f * fs; }
+    for (int f = f0; f < f1; ++f) { in[f - f0] = p->xa + f * p->xa_stride(); out[f - f0] = p->wfield(f); }
     ProfScope ps(PC_Z_FWD, s);
     return b2i_slab_zpass(p, -1, in, out, f1 - f0, s);
 }

@@ -40,6 +40,22 @@ struct b2_plan {
     int gyk_lo, gyk_hi;  // global dealiased ky band (pruned slab y passes)
     int slab_nc;         // z chunks of the exchange layout (b2_slab_set_chunks)
     int ky_cyclic;       // ky rows dealt round-robin to the ranks (balances the pruned K side)
+    // sparse forcing (b2_set_forcing_sparse): forcing_fft of the current time step, added to the raw
+    // nonlinear term of every stage before projection / dealiasing
+    long long force_n;
+    const long long* force_idx;
+    const cplx* force_val;
+    int force_nvar;
+    long long xa_fs, xb_fs;  // elements between consecutive fields of xa / xb (0: fsize())
+    // memory-lean buffers (b2_set_aliasing, ns3d): the raw transform outputs live in `stage`
+    // (the epilogue rewrites them in place into the next stage input), `work` holds only omega (3 fields)
+    int alias_tw;
+    cplx* wfield(int f) const {  // work-field slot f: 0..2 = v / raw outputs, 3..5 = omega, 6 = b
+        if (!alias_tw) return work + (long long)f * fsize();
+        return f < 3 ? stage + (long long)f * fsize() : work + (long long)(f - 3) * fsize();
+    }
+    long long xa_stride() const { return xa_fs > 0 ? xa_fs : fsize(); }
+    long long xb_stride() const { return xb_fs > 0 ? xb_fs : fsize(); }
     long long fsize() const { return (long long)n0 * n1 * nk; }  // complex elements per K field
     long long xsize() const { return (long long)n0 * n1 * n2; }
 };

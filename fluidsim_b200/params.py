@@ -97,7 +97,23 @@ def create_default_params(solver="ns3d"):
             max_elapsed=None,
         ),
     )
-    p._set_child("forcing", dict(enable=False))
+    # base/forcing/base.py:63-76, 189-196; specific.py:436-451, 777-786
+    p._set_child(
+        "forcing",
+        dict(
+            enable=False,
+            type="",
+            available_types=["in_script", "proportional", "tcrandom"],
+            forcing_rate=1.0,
+            key_forced=None,
+            nkmax_forcing=5,
+            nkmin_forcing=4,
+            random_seed=None,
+        ),
+    )
+    p.forcing._set_child("normalized", dict(type="2nd_degree_eq", which_root="minabs", constant_rate_of=None))
+    p.forcing._set_child("random", dict(only_positive=False))
+    p.forcing._set_child("tcrandom", dict(time_correlation="based_on_forcing_rate"))
     p._set_child("init_fields", dict(type="constant"))
     p.init_fields._set_child("noise", dict(velo_max=1.0, length=None))
     return p

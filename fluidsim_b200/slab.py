@@ -88,7 +88,7 @@ class SlabSimul:
     state is ``state_spect`` of shape ``(nvar, ny_loc, nz, nk)``.
     """
 
-    def __init__(self, solver, params, group=None, ky_distribution="auto"):
+    def __init__(self, solver, params, group=None, ky_distribution="auto", lean=None):
         import torch
         import torch.distributed as dist
 
@@ -131,9 +131,24 @@ class SlabSimul:
         self.nwork = self.nvar + 3
         self.nout = 3 if solver == "ns3d" else 6
         mk = lambda n: torch.zeros((n,) + self.shapeK_loc, dtype=torch.complex128, device=self.device)
+        # Memory-lean mode (what makes 2048^3 fit 8 x 180 GB): exchange buffers sized for the PRUNED
+        # exchange (allocated once the mask is known: ny * nz_loc * keepx and kept_ky * nz_loc * keepx
+        # elements per field instead of a full K field each) and, for ns3d, the raw transform outputs
+        # aliased with the stage buffer (work holds the 3 vorticity fields only).  Local K fields:
+        # 27 -> 18.7 (ns3d).  The price: every state handed to the stepper must already be dealiased
+        # (checked on the device), and tendencies_nonlin on arbitrary input is refused.
+        if lean is None:
+            lean = os.environ.get("B2_SLAB_LEAN", "0") not in ("0", "")
+        self.lean = bool(lean)
         self.state_spect = mk(self.nvar)
         self._acc, self._stagebuf = mk(self.nvar), mk(self.nvar)
-        self._work, self._xa, self._xb = mk(self.nwork), mk(self.nwork), mk(self.nwork)
+        self._alias = self.lean and solver == "ns3d"
+        self._work = mk(3 if self._alias else self.nwork)
+        if self.lean:
+            self._xa = self._xb = None  # allocated by _alloc_exchange() when the mask is set
+        else:
+            self._xa, self._xb = mk(self.nwork), mk(self.nwork)
+        self._xa_fs = self._xb_fs = int(np.prod(self.shapeK_loc))
         self.where_dealiased = None  # local uint8 mask (ny_loc, nz, nk); set_mask_from_global
         self.deltat = float(params.time_stepping.deltat0)
         self.scheme = params.time_stepping.type_time_scheme
@@ -165,7 +180,10 @@ class SlabSimul:
              float(p.nu_8), float(p.nu_m4), 0 if f is None else 1, 0.0 if f is None else float(f),
              float(getattr(p, "N", 0.0)), 0.0, ptr(self.where_dealiased))
         call("b2_set_buffers", self.handle, ptr(self._acc), ptr(self._stagebuf), ptr(self._work))
-        call("b2_slab_set_buffers", self.handle, ptr(self._xa), ptr(self._xb))
+        call("b2_set_aliasing", self.handle, 1 if self._alias else 0)
+        if self._xa is not None:
+            call("b2_slab_set_buffers", self.handle, ptr(self._xa), ptr(self._xb))
+            call("b2_slab_set_buffer_strides", self.handle, self._xa_fs, self._xb_fs)
 
     # ---- data in / out ---------------------------------------------------------------------------
     def set_mask_from_global(self, mask_global):
@@ -177,6 +195,29 @@ class SlabSimul:
         self.where_dealiased = mask_local.contiguous()
         self._push()
         self._setup_pruning()
+        if self.lean:
+            self._alloc_exchange()
+
+    def _alloc_exchange(self):
+        """Lean mode: exchange buffers of the pruned exchange only."""
+        from ._lib import call, ptr
+
+        if self._prune is None:
+            raise ValueError("lean slab buffers need a dealiasing mask (pruned exchange)")
+        keepx, kz_lo, kz_hi, yl_lo, yl_hi, gy_lo, gy_hi = self._prune["args"]
+        nyk = self.ny - (gy_hi - gy_lo)
+        self._xa_fs = self.ny * self.nzl * keepx
+        self._xb_fs = nyk * self.nzl * keepx
+        tr = self.torch
+        self._xa = self._xb = None
+        self._xa = tr.zeros(self.nwork * self._xa_fs, dtype=tr.complex128, device=self.device)
+        self._xb = tr.zeros(self.nwork * self._xb_fs, dtype=tr.complex128, device=self.device)
+        call("b2_slab_set_buffers", self.handle, ptr(self._xa), ptr(self._xb))
+        call("b2_slab_set_buffer_strides", self.handle, self._xa_fs, self._xb_fs)
+
+    def _field(self, buf, f, stride):
+        """Field f of an exchange buffer (lean buffers are flat, the others (nwork, ny_loc, nz, nk))."""
+        return buf[f] if buf.dim() > 1 else buf[f * stride:(f + 1) * stride]
 
     def set_state_from_global(self, state_global):
         loc = local_from_global(np.asarray(state_global), self.rank, self.world, self.cyclic)
@@ -301,6 +342,9 @@ class SlabSimul:
 
         h = self.handle
         pr = self._prune if (prune and self._prune is not None) else None
+        if pr is None and self.lean:
+            raise ValueError("lean slab buffers hold the pruned exchange only: the input must be dealiased "
+                             "(SlabSimul(..., lean=False) handles arbitrary states)")
         if pr is None:
             call("b2_slab_set_pruning", h, 0, 0, 0, 0, 0, 0, 0, 0)
         else:
@@ -309,7 +353,8 @@ class SlabSimul:
         call("b2_slab_set_chunks", h, nc)
         ex = self._exchange_plan(pr)
         sp = stream_ptr()
-        xa, xb = self._xa, self._xb
+        XA = lambda f: self._field(self._xa, f, self._xa_fs)
+        XB = lambda f: self._field(self._xb, f, self._xb_fs)
         asyn = self.pipelined
         order = list(range(self.nwork))
         if need_curl:  # v (and b) first: they do not depend on the curl kernel
@@ -321,10 +366,10 @@ class SlabSimul:
                 call("b2_slab_curl", h, ptr(Sin), sp)
                 curl_done = True
             call("b2_slab_zinv", h, ptr(Sin), f, f + 1, sp)
-            inv[(f, 0)] = self._a2a(xa[f], xb[f], 0, 0, ex["mine"], ex["theirs"], asyn)
+            inv[(f, 0)] = self._a2a(XA(f), XB(f), 0, 0, ex["mine"], ex["theirs"], asyn)
         for c in range(1, nc):
             for f in order:
-                inv[(f, c)] = self._a2a(xa[f], xb[f], c * ex["cs_a"], c * ex["cs_b"], ex["mine"], ex["theirs"], asyn)
+                inv[(f, c)] = self._a2a(XA(f), XB(f), c * ex["cs_a"], c * ex["cs_b"], ex["mine"], ex["theirs"], asyn)
         fwd = {}
         for c in range(nc):
             for f in order:
@@ -334,7 +379,7 @@ class SlabSimul:
             call("b2_slab_xpass", h, c, sp)
             for f in range(self.nout):
                 call("b2_slab_yfwd", h, f, f + 1, c, sp)
-                fwd[(f, c)] = self._a2a(xb[f], xa[f], c * ex["cs_b"], c * ex["cs_a"], ex["theirs"], ex["mine"], asyn)
+                fwd[(f, c)] = self._a2a(XB(f), XA(f), c * ex["cs_b"], c * ex["cs_a"], ex["theirs"], ex["mine"], asyn)
         for f in range(self.nout):
             if asyn:
                 for c in range(nc):
@@ -343,6 +388,8 @@ class SlabSimul:
         call("b2_slab_rk", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout), sp)
 
     def tendencies_nonlin(self, state_spect=None, old=None):
+        if self.lean:
+            raise ValueError("tendencies_nonlin on arbitrary input needs the full-size buffers (lean=False)")
         src = self.state_spect if state_spect is None else state_spect
         out = self.torch.empty_like(self.state_spect) if old is None else old
         self._run_stage(src, True, SCHEME_IDS[self.scheme], -1, out)
@@ -351,6 +398,8 @@ class SlabSimul:
     def one_time_step(self):
         sid = SCHEME_IDS[self.scheme]
         nstages = 4 if self.scheme == "RK4" else 2
+        if self.use_pruning and not self._state_dealiased and self.where_dealiased is not None:
+            self._state_dealiased = self._check_dealiased()
         prune = self.use_pruning and self._state_dealiased
         for st in range(nstages):
             Sin = self.state_spect if st == 0 else self._stagebuf
@@ -358,6 +407,17 @@ class SlabSimul:
         self._state_dealiased = True  # the last stage projects and dealiases the state
         self.t += self.deltat
         self.it += 1
+
+    def _check_dealiased(self):
+        """Is the local state exactly zero wherever the mask dealiases, on every rank?"""
+        from ._lib import call, ptr, stream_ptr
+
+        tr = self.torch
+        flag = tr.zeros(1, dtype=tr.int32, device=self.device)
+        call("b2_check_dealiased", self.handle, ptr(self.state_spect), self.nvar, ptr(self.where_dealiased),
+             ptr(flag), stream_ptr())
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(flag.item()) == 0
 
     def compute_energy(self):
         """sum_wavenumbers(|v|^2)/2 over the velocity components, all-reduced."""

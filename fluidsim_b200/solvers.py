@@ -33,8 +33,6 @@ class SimulBasePseudoSpectralB200:
     def __init__(self, params, fused=None):
         self.params = params
         self.is_forcing_enabled = bool(getattr(params.forcing, "enable", False))
-        if self.is_forcing_enabled:
-            raise NotImplementedError("forcing is outside the GPU hot path (SURVEY.md section 8 f-2)")
         self.oper = self.Operators(params)
         self.state = self.State(self)
         self._init_projection()
@@ -45,6 +43,12 @@ class SimulBasePseudoSpectralB200:
         self.use_pruning = True
         self._state_dealiased = False
         self.time_stepping = self.TimeStepping(self, fused=fused)
+        # base/solvers/base.py:190-195: the forcing object comes after the time stepper
+        self.forcing = None
+        if self.is_forcing_enabled:
+            from .forcing import ForcingB200
+
+            self.forcing = ForcingB200(self)
 
     def _init_projection(self):
         pass
@@ -76,13 +80,19 @@ class SimulBasePseudoSpectralB200:
 
         nwork, nvar = C.c_int(), C.c_int()
         call("b2_work_fields", h, SOLVER_IDS[self.short_name], C.byref(nwork), C.byref(nvar))
+        # ns3d: the raw transform outputs are aliased with the stage buffer (b2_set_aliasing), so the
+        # work buffer holds the 3 vorticity fields only: 12 K fields per GPU instead of 15
+        import os
+
+        alias = self.short_name == "ns3d" and os.environ.get("B2_NOALIAS", "0") in ("0", "")
         if self._fused_buffers is None:
             mk = lambda n: torch.empty((n,) + tuple(oper.shapeK_loc), dtype=torch.complex128, device=oper.device)
-            self._fused_buffers = (mk(nvar.value), mk(nvar.value), mk(nwork.value))
+            self._fused_buffers = (mk(nvar.value), mk(nvar.value), mk(3 if alias else nwork.value))
         acc, stage, work = self._fused_buffers
         self._fused_mask = mask
         call("b2_set_physics", h, SOLVER_IDS[self.short_name], *self._physics_args(), ptr(mask))
         call("b2_set_buffers", h, ptr(acc), ptr(stage), ptr(work))
+        call("b2_set_aliasing", h, 1 if alias else 0)
 
     def mask_modified(self):
         """Call after editing ``oper.where_dealiased`` in place: the kept ranges of the pruned
@@ -195,6 +205,8 @@ class SimulNS3D(SimulBasePseudoSpectralB200):
         fft_as_arg(fy, tendencies_fft.get_var("vy_fft"))
         fft_as_arg(fz, tendencies_fft.get_var("vz_fft"))
         self._extra_tendencies(tendencies_fft, spect_get_var, state_spect, vx, vy, vz)
+        if self.is_forcing_enabled:  # solver.py:243-244
+            tendencies_fft += self.forcing.get_forcing()
         self.project_state_spect(tendencies_fft)
         self.oper.dealiasing(tendencies_fft)
         return tendencies_fft
@@ -277,6 +289,8 @@ class SimulNS2D(SimulBasePseudoSpectralB200):
         Frot_fft = tendencies_fft.get_var("rot_fft")
         oper.fft_as_arg(px_rot, Frot_fft)
         oper.dealiasing(Frot_fft)
+        if self.params.forcing.enable:  # ns2d/solver.py:190-191
+            tendencies_fft += self.forcing.get_forcing()
         return tendencies_fft
 
 

@@ -170,6 +170,8 @@ class TimeSteppingPseudoSpectralB200:
     def one_time_step(self):
         if self.params.time_stepping.USE_CFL and not self.fused:
             self.compute_time_increment_CLF()  # fused path: decided on the device inside the step
+        if self.sim.is_forcing_enabled:  # base.py:212-213
+            self.sim.forcing.compute()
         if self.max_elapsed is not None and time() > self._time_should_stop:
             self._has_to_stop = True
         if self._stop_signal_received:

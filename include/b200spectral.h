@@ -135,6 +135,19 @@ int b2_get_pruning_bounds(const b2_plan* p, int* out);
 int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar);
 /* caller-owned buffers: acc, stage (each nvar K-fields), work (nwork K-fields) */
 int b2_set_buffers(b2_plan* p, double* acc, double* stage, double* work);
+/* memory-lean ns3d (call after b2_set_physics): the raw transform outputs are written into `stage`
+ * and rewritten in place by the RK epilogue, so `work` needs only 3 K fields (the vorticity of the
+ * next stage input): 12 instead of 15 K fields per GPU.  The reference keeps the same data in
+ * state_spect + 2 tmp sets + fields_tmp[6] + fields_spect_tmp[3] (solvers/ns3d/state.py:46-52). */
+int b2_set_aliasing(b2_plan* p, int on);
+/* forcing: `tendencies_fft += self.forcing.get_forcing()` (solvers/ns3d/solver.py:243-244,
+ * ns2d/solver.py:185-186).  The forcing makers of base/forcing/specific.py:137-345 act on at most
+ * (2 nkmax_forcing)^3 low-wavenumber modes, so forcing_fft is passed as a sparse list: idx = nmodes
+ * linear indices into a K field (device int64), val = nvar x nmodes complex128 (device), nvar leading
+ * state variables.  The plan keeps the pointers (caller-owned, valid until replaced); every stage of
+ * the following steps adds the list to the raw nonlinear term before projection and dealiasing.
+ * nmodes = 0 switches forcing off. */
+int b2_set_forcing_sparse(b2_plan* p, long long nmodes, const long long* idx, const double* val, int nvar);
 /* T_out = N(S_in)  (projected + dealiased).  S_in is preserved; T_out may not alias S_in. */
 int b2_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream);
 /* one full step of `scheme` with time increment dt, in place on S, including the final
@@ -153,6 +166,10 @@ int b2_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
 int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double Lz, double Ly, double Lx, int rank,
                         int nranks, int ky_cyclic);
 int b2_slab_set_buffers(b2_plan* p, double* xa, double* xb);
+/* complex elements between consecutive fields of xa / xb (default: one full K field).  With the
+ * pruned exchange (b2_slab_set_pruning) only b2_slab_buffer_need elements per field are touched. */
+int b2_slab_set_buffer_strides(b2_plan* p, long long xa_field, long long xb_field);
+int b2_slab_buffer_need(const b2_plan* p, long long* xa_field, long long* xb_field);
 /* pruned exchange (see b2_set_pruning): kept ranges agreed between the ranks by the host side; the
  * all-to-alls then carry only the kept local ky rows x kx < keepx (uneven splits) */
 int b2_slab_set_pruning(b2_plan* p, int on, int keepx, int kz_lo, int kz_hi, int yl_lo, int yl_hi,

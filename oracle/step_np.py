@@ -102,6 +102,9 @@ class OracleSim:
         self.scheme = type_time_scheme
         self.it = 0
         self.t = 0.0
+        # forcing_fft of the current step (same shape as state_spect) or None; the reference adds
+        # `self.forcing.get_forcing()` to the tendencies (solvers/ns3d/solver.py:243-244)
+        self.forcing_fft = None
         if solver == "ns2d":
             self.ndim = 2
             self.oper = OperatorsPseudoSpectral2D(nx, ny, Lx, Ly, coef_dealiasing=coef_dealiasing)
@@ -254,6 +257,8 @@ class OracleSim:
             # compute_fb_fft, strat/solver.py:29-33
             fb_fft = -div_vb_fft - self.N**2 * vz_fft
             tendencies_fft.set_var("b_fft", fb_fft)
+        if self.forcing_fft is not None:  # solvers/ns3d/solver.py:243-244
+            tendencies_fft += self.forcing_fft
         self.project_state_spect(tendencies_fft)
         self.dealiasing(tendencies_fft)
         return tendencies_fft
@@ -286,6 +291,8 @@ class OracleSim:
         Frot_fft = tendencies_fft.get_var("rot_fft")
         oper.fft_as_arg(Frot, Frot_fft)
         self.dealiasing(Frot_fft)
+        if self.forcing_fft is not None:  # solvers/ns2d/solver.py:190-191 (after the dealiasing)
+            tendencies_fft += self.forcing_fft
         return tendencies_fft
 
     # ------------------------------------------------------------------ schemes

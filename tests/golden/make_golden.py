@@ -36,12 +36,48 @@ CASES = {
     "ns2d_32x32_rk4": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
     "ns2d_64x32_rk2_beta": ("ns2d", (64, 32), 5, dict(nu_2=1e-3, deltat0=1e-2, beta=0.4, type_time_scheme="RK2", Lx=8.0, Ly=8.0)),
     "ns2d_24x15_rk4_odd": ("ns2d", (24, 15), 3, dict(nu_2=1e-3, deltat0=2e-2, Lx=8.0, Ly=8.0, truncation_shape="no_multiple_aliases")),
+    # forced cases: a constant forcing_fft on the shell 2 <= |k|/dk <= 3.5 handed to the reference's
+    # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
+    "ns3d_16x16x16_rk4_forced": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),
+    "strat_16x16x16_rk4_forced": ("ns3d.strat", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, N=2.0)),
+    "ns2d_32x32_rk4_forced": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
 }
+
+
+def make_forcing(o, seed=7):
+    """Deterministic forcing_fft: random complex amplitudes on the kept modes of the shell
+    2 <= |k| / deltak <= 3.5 of the velocity components (ns2d: of rot_fft); zero elsewhere."""
+    oper = o.oper
+    rng = np.random.default_rng(seed)
+    K = np.sqrt(oper.K2)
+    dk = max(getattr(oper, "deltakx"), getattr(oper, "deltaky"), getattr(oper, "deltakz", 0.0))
+    shell = (K >= 2 * dk) & (K <= 3.5 * dk) & (np.asarray(oper.where_dealiased) == 0)
+    f = np.zeros(o.state_spect.shape, dtype=np.complex128)
+    nforced = 1 if o.solver == "ns2d" else 3
+    for v in range(nforced):
+        amp = rng.standard_normal(K.shape) + 1j * rng.standard_normal(K.shape)
+        f[v][shell] = 0.05 * amp[shell]
+    return f
+
+
+class _StubForcing:
+    """What the reference's tendencies_nonlin needs from sim.forcing."""
+
+    def __init__(self, forcing_fft):
+        self.forcing_fft = forcing_fft
+
+    def get_forcing(self):
+        return self.forcing_fft
+
+    def compute(self):
+        pass
 
 
 def main():
     outdir = os.path.dirname(os.path.abspath(__file__))
     for name, (solver, shape, nsteps, kw) in CASES.items():
+        if os.path.exists(os.path.join(outdir, name + ".npz")) and "--all" not in sys.argv:
+            continue  # committed fixtures are kept byte-identical; --all regenerates everything
         nx, ny = shape[0], shape[1]
         nz = shape[2] if len(shape) == 3 else None
         # initial condition: the reference's noise recipe (restated in step_np.init_noise, which
@@ -52,6 +88,15 @@ def main():
         params = refshim.make_params(solver, nx, ny, nz, **kw)
         ref = refshim.RefSim(solver, params)
         ref.set_state_spect(s0)
+        extra = {}
+        if name.endswith("_forced"):
+            forcing = make_forcing(o)
+            sov = type(ref.sim.state.state_spect)(like=ref.sim.state.state_spect, value=0.0)
+            sov[...] = forcing
+            ref.sim.is_forcing_enabled = True
+            ref.sim.params.forcing.enable = True
+            ref.sim.forcing = _StubForcing(sov)
+            extra["forcing"] = forcing
         mask = np.array(ref.oper.where_dealiased)
         tend0 = np.array(ref.sim.tendencies_nonlin())
         states = []
@@ -69,6 +114,7 @@ def main():
             stateN=states[-1],
             energyN=e.compute_energy(),
             enstrophyN=e.compute_enstrophy(),
+            **extra,
         )
         print(name, "ok", s0.shape)
 

@@ -13,6 +13,8 @@ def test_oracle_matches_golden(name):
     o = make_oracle(meta)
     assert np.array_equal(o.oper.where_dealiased, z["mask"])
     o.set_state_spect(z["state0"])
+    if "forcing" in z.files:  # forced goldens: tendencies += forcing_fft (solvers/ns3d/solver.py:243-244)
+        o.forcing_fft = z["forcing"]
     tend = np.array(o.tendencies_nonlin())
     assert rel_err(tend, z["tend0"]) < 1e-13
     o.one_time_step()
@@ -110,3 +112,13 @@ def test_cfl_rule_equals_reference_code():
         dt_o = o.compute_time_increment_CFL(cfl=1.0, deltat_max=0.2)
         assert ts.deltat == dt_o
         o.one_time_step()
+
+
+def test_forced_goldens_differ_from_the_unforced_run():
+    """The forcing really acts in the forced fixtures (same initial state as the unforced case)."""
+    for forced, plain in (("ns3d_16x16x16_rk4_forced", "ns3d_16x16x16_rk4"), ("ns2d_32x32_rk4_forced", "ns2d_32x32_rk4")):
+        _, zf = load_golden(forced)
+        _, zp = load_golden(plain)
+        assert np.array_equal(zf["state0"], zp["state0"])
+        assert np.abs(zf["forcing"]).max() > 0
+        assert rel_err(zf["state1"], zp["state1"]) > 1e-4

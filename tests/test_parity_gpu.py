@@ -493,3 +493,98 @@ def test_state_edits_through_the_reference_idioms_drop_pruning():
     _ = sim.state.state_phys
     _ = sim.state.compute_energy_spect()
     assert sim._state_dealiased
+
+
+# ------------------------------------------------------------------ forcing
+def _forced_sim(meta, z, fused):
+    """GPU Simul with an in_script forcing that returns the golden's constant forcing_fft."""
+    import torch
+
+    from fluidsim_b200.solvers import SIMUL_CLASSES
+
+    sim0 = make_gpu_sim(meta, fused=fused, mask=z["mask"])
+    p = sim0.params
+    p.forcing.enable = True
+    p.forcing.type = "in_script"
+    sim = SIMUL_CLASSES[meta["solver"]](p, fused=fused)
+    sim.oper.where_dealiased = torch.from_numpy(np.ascontiguousarray(z["mask"])).to(sim.oper.device)
+    keys = sim.state.keys_state_spect
+    forcing = z["forcing"]
+
+    def compute_forcing_fft_each_time(self):
+        return {key: torch.from_numpy(np.ascontiguousarray(forcing[i])).to(sim.oper.device)
+                for i, key in enumerate(keys) if np.abs(forcing[i]).max() > 0}
+
+    sim.forcing.forcing_maker.monkeypatch_compute_forcing_fft_each_time(compute_forcing_fft_each_time)
+    return sim
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4_forced", "strat_16x16x16_rk4_forced", "ns2d_32x32_rk4_forced"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_forced_step_matches_reference_golden(name, fused):
+    """`tendencies_fft += forcing.get_forcing()` (/root/reference/fluidsim/solvers/ns3d/solver.py:243-244,
+    strat/solver.py:210-211, ns2d/solver.py:190-191): golden made by the reference's own
+    tendencies_nonlin with a stub forcing object (tests/golden/make_golden.py)."""
+    meta, z = load_golden(name)
+    sim = _forced_sim(meta, z, fused)
+    assert sim.time_stepping.fused == fused
+    set_state(sim, z["state0"])
+    sim.forcing.compute()
+    if fused:
+        tend = sim.tendencies_nonlin_fused().numpy()
+    else:
+        tend = sim.tendencies_nonlin().numpy()
+    assert rel_err(tend, z["tend0"]) < TOL_STEP
+    sim.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), z["state1"]) < TOL_STEP
+    for _ in range(meta["nsteps"] - 1):
+        sim.time_stepping.one_time_step()
+    assert rel_err(sim.state.state_spect.numpy(), z["stateN"]) < 10 * TOL_STEP
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ftype", ["tcrandom", "proportional"])
+def test_normalised_forcing_injects_the_prescribed_rate(ftype):
+    """Forced isotropic turbulence set-up of BASELINE config 3 (doc/examples/simul_ns3d_forced_isotropic.py)
+    at 64^3: the normalised forcing must satisfy the injection identity of
+    normalize_forcingc_2nd_degree_eq (/root/reference/fluidsim/base/forcing/specific.py:587-677),
+    sum' Re(conj(v) f) + dt/2 sum' |f|^2 = forcing_rate, every step, and energy must grow accordingly."""
+    from fluidsim_b200.solvers import SimulNS3D
+
+    p = SimulNS3D.create_default_params()
+    p.oper.nx = p.oper.ny = p.oper.nz = 64
+    p.nu_2 = 1e-3
+    p.time_stepping.USE_CFL = False
+    p.time_stepping.deltat0 = 5e-3
+    p.forcing.enable = True
+    p.forcing.type = ftype
+    p.forcing.nkmin_forcing = 3
+    p.forcing.nkmax_forcing = 4
+    p.forcing.forcing_rate = 0.5
+    p.forcing.random_seed = 3
+    sim = SimulNS3D(p, fused=True)
+    o = make_oracle(dict(solver="ns3d", shape=(64, 64, 64), params=dict(nu_2=1e-3, deltat0=5e-3)))
+    o.init_noise()
+    set_state(sim, 0.3 * np.array(o.state_spect))
+    oper = sim.oper
+    e0 = sim.state.compute_energy_spect()
+    dt = sim.time_stepping.deltat
+    for it in range(4):
+        sim.time_stepping.one_time_step()
+        # identity on the forcing used for the step just done (state before the step is gone:
+        # recompute with the current state through the maker, which is what the next step will use)
+        sim.forcing._t_last_computed = -np.inf
+        sim.forcing.compute()
+        f = sim.forcing.get_forcing().tensor[:3]
+        v = sim.state.state_spect.tensor[:3]
+        p1 = sum(oper.sum_wavenumbers((f[i].conj() * v[i]).real) for i in range(3))
+        p2 = dt / 2 * sum(oper.sum_wavenumbers(f[i].abs() ** 2) for i in range(3))
+        if ftype == "tcrandom":
+            assert abs(p1 + p2 - 0.5) < 1e-10
+        else:  # proportional: Z ((1 + alpha dt)^2 - 1) / dt = P with Z the shell energy
+            assert abs(p1 + p2 - 0.5) < 1e-10
+        # the forcing is solenoidal and sits on kept low-wavenumber modes only
+        div = oper.divfft_from_vecfft(f[0], f[1], f[2])
+        assert float(div.abs().max()) < 1e-12
+    assert sim.state.compute_energy_spect() > e0

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, name, nchunks, dist_kind, q):
+def _worker(rank, world, port, name, nchunks, dist_kind, lean, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     sys.path.insert(0, ROOT)
@@ -38,18 +38,24 @@ def _worker(rank, world, port, name, nchunks, dist_kind, q):
         p.time_stepping.deltat0 = kw.pop("deltat0")
         for key in list(kw):
             setattr(p, key, kw.pop(key))
-        sim = SlabSimul(solver, p, ky_distribution=dist_kind)
+        sim = SlabSimul(solver, p, ky_distribution=dist_kind, lean=lean)
         if nchunks and sim.nzl % nchunks == 0:
             sim.nchunks = nchunks
         sim.set_mask_from_global(z["mask"])
         sim.set_state_from_global(z["state0"])
-        tend = sim.tendencies_nonlin()
-        parts = [torch.empty_like(tend) for _ in range(world)]
-        dist.all_gather(parts, tend)
-        from fluidsim_b200.slab import global_from_local
+        if lean:
+            # memory-lean buffers (pruned exchange only, raw outputs aliased with the stage buffer)
+            e_t = 0.0
+            with pytest.raises(ValueError):
+                sim.tendencies_nonlin()
+        else:
+            tend = sim.tendencies_nonlin()
+            parts = [torch.empty_like(tend) for _ in range(world)]
+            dist.all_gather(parts, tend)
+            from fluidsim_b200.slab import global_from_local
 
-        e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts], sim.cyclic), z["tend0"])
-        sim.one_time_step()  # unpruned (state not known to be dealiased)
+            e_t = rel_err(global_from_local([t.cpu().numpy() for t in parts], sim.cyclic), z["tend0"])
+        sim.one_time_step()  # the golden initial states are dealiased: recognised on the device, pruned
         assert sim._prune is not None
         e_1 = rel_err(sim.gather_state(), z["state1"])
         for _ in range(meta["nsteps"] - 1):
@@ -62,9 +68,11 @@ def _worker(rank, world, port, name, nchunks, dist_kind, q):
 
 
 @pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4", "ns3d_32x16x8_rk2_f", "strat_16x16x16_rk4", "strat_16x8x32_rk2"])
-@pytest.mark.parametrize("world,nchunks,dist_kind", [(2, 1, "block"), (2, 2, "cyclic"), (4, 2, "cyclic"),
-                                                     (8, 1, "cyclic"), (8, 2, "block")])
-def test_slab_matches_reference_golden(name, world, nchunks, dist_kind):
+@pytest.mark.parametrize("world,nchunks,dist_kind,lean", [(2, 1, "block", False), (2, 2, "cyclic", False),
+                                                          (2, 2, "block", True), (4, 2, "cyclic", False),
+                                                          (8, 1, "cyclic", False), (8, 2, "block", False),
+                                                          (8, 2, "cyclic", True)])
+def test_slab_matches_reference_golden(name, world, nchunks, dist_kind, lean):
     import torch
     import torch.multiprocessing as mp
 
@@ -76,8 +84,8 @@ def test_slab_matches_reference_golden(name, world, nchunks, dist_kind):
         pytest.skip("grid not divisible")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() + world * 7 + nchunks * 3 + len(name)) % 300
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, nchunks, dist_kind, q)) for r in range(world)]
+    port = 29600 + (os.getpid() + world * 7 + nchunks * 3 + len(name) + 11 * int(lean)) % 300
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, nchunks, dist_kind, lean, q)) for r in range(world)]
     for pr in procs:
         pr.start()
     for pr in procs:
