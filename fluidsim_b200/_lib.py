@@ -58,6 +58,8 @@ SIGNATURES = {
     "b2_rk4_step2": [_p, _p, _p, _p, _p, _p, _p, _d, _i, _p],
     "b2_rk4_step3": [_p, _p, _p, _p, _d, _i, _p],
     "b2_sum_wavenumbers_abs2": [_p, _p, _i, _p, _p],
+    "b2_observables_size": [_p, _i, _i],
+    "b2_observables": [_p, _p, _i, _i, _d, _p, _p],
     "b2_max_abs": [_p, _ll, _p, _p],
     "b2_sum": [_p, _ll, _p, _p],
     "b2_set_physics": [_p, _i, _d, _d, _d, _d, _i, _d, _d, _d, _p],
@@ -93,7 +95,7 @@ SIGNATURES = {
     "b2_profile_get": [C.POINTER(_d), C.POINTER(_ll), _i],
     "b2_dev_strided_pass": [_p, _i, _i, _p, _p, _i, _p],
 }
-_RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": _ll}
+_RESTYPES = {"b2_last_error": C.c_char_p, "b2_launch_count": _ll, "b2_observables_size": _ll}
 
 for _name, _args in SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError if the symbol is not exported

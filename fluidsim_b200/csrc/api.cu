@@ -714,6 +714,168 @@ extern "C" int b2_sum(const double* x, long long n, double* out_dev, void* strea
 }
 
 
+// ------------------------------------------------------------------------------- observables
+// One pass over the state for everything the reference's periodic outputs reduce from it:
+// component energies, dissipation rates, enstrophy (SpatialMeansNS3D._save_one_time,
+// /root/reference/fluidsim/solvers/ns3d/output/spatial_means.py:23-73), the shell-binned 3-D spectra
+// and the 1-D spectra of every component (SpectraNS3D.compute, output/spectra.py:15-60, through
+// fluidfft's compute_3dspectrum / compute_1dspectra [EXT]: r2c weights, linear sharing between
+// adjacent shells, +-k folded in the 1-D spectra).  A few persistent CTAs walk over the (i0, i1)
+// rows; histograms live in shared memory and are flushed once per CTA with atomicAdd.
+//
+// out (doubles):  [0..3]  E of variable 0..3 (sum' |a|^2 / 2)        [4] epsK   [5] epsK_hypo
+//                 [6] epsK4   [7] epsK8   [8] enstrophy (sum' |k x v|^2 / 2, 3-D)   [9..15] reserved
+//                 then spec3d[nvar][nks], s_kx[nvar][nkx1], s_ky[nvar][nky1], s_kz[nvar][nkz1]
+//                 (already divided by deltak / deltakx / deltaky / deltakz)
+#define B2_OBS_SCALARS 16
+struct ObsArgs {
+    KGrid g;
+    Visc visc;
+    const cplx* S;
+    long long fsize;
+    int nvar, nks, nkx1, nky1, nkz1, nx_even, is3d;
+    double inv_dk, inv_dkx, inv_dky, inv_dkz;
+    long long nrows;
+    double* out;
+};
+__global__ void __launch_bounds__(B2_ROW_THREADS) observables_kernel(ObsArgs a) {
+    extern __shared__ double obs_sm[];
+    const KGrid& g = a.g;
+    const int nv = a.nvar;
+    double* sp3 = obs_sm;                       // [nv][nks]
+    double* skx = sp3 + (size_t)nv * a.nks;     // [nv][nkx1]
+    double* sky = skx + (size_t)nv * a.nkx1;    // [nv][nky1]
+    double* skz = sky + (size_t)nv * a.nky1;    // [nv][nkz1]
+    const int ntot = nv * (a.nks + a.nkx1 + a.nky1 + a.nkz1);
+    for (int i = threadIdx.x; i < ntot; i += blockDim.x) obs_sm[i] = 0.0;
+    __syncthreads();
+    double sc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long row = blockIdx.x; row < a.nrows; row += gridDim.x) {
+        const int i0 = (int)(row / g.n1), i1 = (int)(row - (long long)i0 * g.n1);
+        const double K0v = g.k0[i0], K1v = g.k1[i1];
+        const double Kz = a.is3d ? (g.swap01 ? K1v : K0v) : 0.0;
+        const double Ky = g.swap01 ? K0v : K1v;
+        const bool row_origin = g.has_origin && i0 == 0 && i1 == 0;
+        const long long rbase = ((long long)i0 * g.n1 + i1) * g.nk;
+        const int iky = (int)lrint(fabs(Ky) * a.inv_dky), ikz = (int)lrint(fabs(Kz) * a.inv_dkz);
+        double rowE[4] = {0, 0, 0, 0};
+        for (int ikx = threadIdx.x; ikx < g.nk; ikx += blockDim.x) {
+            const double Kx = g.kx[ikx];
+            const double w = (ikx == 0 || (a.nx_even && ikx == g.nk - 1)) ? 1.0 : 2.0;
+            const double K2 = Kx * Kx + Ky * Ky + Kz * Kz;
+            const double kappa = sqrt(K2) * a.inv_dk;
+            int ik = (int)floor(kappa);
+            double share = kappa - ik;
+            if (ik >= a.nks - 1) { ik = a.nks - 1; share = 0.0; }
+            cplx v3[3] = {make_double2(0, 0), make_double2(0, 0), make_double2(0, 0)};
+            double etot = 0.0;
+            for (int v = 0; v < nv; ++v) {
+                const cplx q = a.S[v * a.fsize + rbase + ikx];
+                if (v < 3) v3[v] = q;
+                const double e = 0.5 * w * (q.x * q.x + q.y * q.y);
+                if (e != 0.0) {
+                    atomicAdd(&sp3[v * a.nks + ik], (1.0 - share) * e);
+                    if (share != 0.0) atomicAdd(&sp3[v * a.nks + ik + 1], share * e);
+                    skx[v * a.nkx1 + ikx] += e;  // slot owned by this thread
+                }
+                rowE[v] += e;
+                sc[v] += e;
+                if (v < 3) etot += e;
+            }
+            const bool origin = row_origin && ikx == 0;
+            const Visc& vs = a.visc;
+            // compute_freq_diss splits f_d (hyper) and f_d_hypo (base/solvers/pseudo_spect.py:161-189)
+            double fd = vs.nu2 > 0.0 ? vs.nu2 * K2 : 0.0;
+            const double K4 = K2 * K2;
+            if (vs.nu4 > 0.0) { fd += vs.nu4 * K4; sc[6] += vs.nu4 * K4 * 2 * etot; }
+            if (vs.nu8 > 0.0) { fd += vs.nu8 * K4 * K4; sc[7] += vs.nu8 * K4 * K4 * 2 * etot; }
+            sc[4] += fd * 2 * etot;
+            if (vs.num4 != 0.0) {
+                const double k2n = origin ? vs.k2_hypo_origin : K2;
+                sc[5] += vs.num4 / (k2n * k2n) * 2 * etot;
+            }
+            if (a.is3d && nv >= 3) {
+                cplx ox, oy, oz;
+                curl3(Kx, Ky, Kz, v3[0], v3[1], v3[2], ox, oy, oz);
+                sc[8] += 0.5 * w * (ox.x * ox.x + ox.y * ox.y + oy.x * oy.x + oy.y * oy.y + oz.x * oz.x + oz.y * oz.y);
+            }
+        }
+        for (int v = 0; v < nv; ++v) {
+            const double r = warp_sum(rowE[v]);
+            if ((threadIdx.x & 31) == 0 && r != 0.0) {
+                atomicAdd(&sky[v * a.nky1 + iky], r);
+                if (a.is3d) atomicAdd(&skz[v * a.nkz1 + ikz], r);
+            }
+        }
+    }
+    __syncthreads();
+    double* o = a.out + B2_OBS_SCALARS;
+    for (int i = threadIdx.x; i < ntot; i += blockDim.x) {
+        const double val = obs_sm[i];
+        if (val != 0.0) {
+            double scale;
+            const int j = i;
+            if (j < nv * a.nks) scale = a.inv_dk;
+            else if (j < nv * (a.nks + a.nkx1)) scale = a.inv_dkx;
+            else if (j < nv * (a.nks + a.nkx1 + a.nky1)) scale = a.inv_dky;
+            else scale = a.inv_dkz;
+            atomicAdd(&o[i], val * scale);
+        }
+    }
+    for (int k = 0; k < 9; ++k) {
+        const double r = warp_sum(sc[k]);
+        if ((threadIdx.x & 31) == 0 && r != 0.0) atomicAdd(&a.out[k], r);
+    }
+}
+
+extern "C" long long b2_observables_size(const b2_plan* p, int nvar, int nks) {
+    const int gy = p->slab ? p->gy : p->n1, gz = p->slab ? p->n1 : p->n0;
+    return B2_OBS_SCALARS + (long long)nvar * (nks + p->nk + (gy / 2 + 1) + (p->ndim == 3 ? gz / 2 + 1 : 1));
+}
+
+extern "C" int b2_observables(b2_plan* p, const double* S, int nvar, int nks, double deltak, double* out_dev,
+                              void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nvar < 1 || nvar > 4) return b2i_set_error("b2_observables: nvar must be in 1..4");
+    if (nks < 2 || deltak <= 0.0) return b2i_set_error("b2_observables: bad shell description");
+    ObsArgs a;
+    a.g = kgrid(p);
+    a.visc = visc_of(p, p->nu2, p->nu4, p->nu8, p->num4);
+    a.S = (const cplx*)S;
+    a.fsize = p->fsize();
+    a.nvar = nvar;
+    a.nks = nks;
+    const int gy = p->slab ? p->gy : p->n1, gz = p->slab ? p->n1 : p->n0;
+    const double Ly = p->slab ? p->L0 : p->L1, Lz = p->slab ? p->L1 : p->L0;
+    a.is3d = p->ndim == 3;
+    a.nkx1 = p->nk;
+    a.nky1 = gy / 2 + 1;
+    a.nkz1 = a.is3d ? gz / 2 + 1 : 1;
+    a.nx_even = p->n2 % 2 == 0;
+    a.inv_dk = 1.0 / deltak;
+    a.inv_dkx = p->L2 / (2.0 * M_PI);
+    a.inv_dky = Ly / (2.0 * M_PI);
+    a.inv_dkz = a.is3d ? Lz / (2.0 * M_PI) : 1.0;
+    a.nrows = (long long)p->n0 * p->n1;
+    a.out = out_dev;
+    const long long ntot = b2_observables_size(p, nvar, nks);
+    CUDA_TRY(cudaMemsetAsync(out_dev, 0, sizeof(double) * ntot, s));
+    const size_t smem = sizeof(double) * (size_t)(ntot - B2_OBS_SCALARS);
+    if (smem > 200 * 1024) return b2i_set_error("b2_observables: histograms do not fit shared memory");
+    if (smem > 48 * 1024) {
+        cudaError_t ce = cudaFuncSetAttribute(observables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return b2i_set_error("observables_kernel: %s", cudaGetErrorString(ce));
+    }
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)nsm * (smem > 100 * 1024 ? 1 : 2);
+    if (grid > a.nrows) grid = a.nrows;
+    observables_kernel<<<(unsigned)grid, B2_ROW_THREADS, smem, s>>>(a);
+    B2_LAUNCH_CHECK("observables_kernel");
+    return 0;
+}
+
 // ------------------------------------------------------------------------------- profiling hooks
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline
 // leg).  Disabled by default: zero overhead unless b2_profile_enable(1) was called.

@@ -246,6 +246,55 @@ class OperatorsPseudoSpectral3D(_OperatorBase):
         spectrum.index_add_(0, torch.where(last, nk - 1, ik + 1), torch.where(last, torch.zeros_like(E), share * E))
         return (spectrum / self.deltak).cpu().numpy()
 
+    def compute_observables(self, fields, nvar=None):
+        """Everything the periodic outputs reduce from ``fields`` (a ``(nvar, *shapeK)`` tensor) in ONE
+        kernel pass (C ABI ``b2_observables``): component energies, dissipation rates, enstrophy,
+        per-component 3-D shell spectra and 1-D spectra.  Returns a dict of floats / numpy arrays with
+        the names of the reference's outputs (solvers/ns3d/output/spatial_means.py:23-73,
+        output/spectra.py:15-60).  The viscosities are the ones last pushed with b2_set_physics."""
+        import ctypes as C
+
+        from ._lib import lib
+
+        t = fields.tensor if hasattr(fields, "tensor") else fields
+        nvar = int(t.shape[0]) if nvar is None else int(nvar)
+        nks = self.nk_spectra
+        h = self.plan.handle
+        n = int(lib.b2_observables_size(h, nvar, nks))
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        call("b2_observables", h, ptr(t), nvar, nks, float(self.deltak), ptr(out), stream_ptr())
+        o = out.cpu().numpy()
+        names = ["vx", "vy", "vz", "b"][:nvar]
+        res = {"E" + ("xyz"[i] if i < 3 else "b"): float(o[i]) for i in range(nvar)}
+        res["E"] = float(sum(o[: min(nvar, 3)]))
+        res.update(epsK=float(o[4]), epsK_hypo=float(o[5]), epsK4=float(o[6]), epsK8=float(o[7]),
+                   enstrophy=float(o[8]))
+        nkx1, nky1, nkz1 = self.nx // 2 + 1, self.ny // 2 + 1, self.nz // 2 + 1
+        pos = 16
+        for nm, ln in (("", nks), ("_kx", nkx1), ("_ky", nky1), ("_kz", nkz1)):
+            for v in range(nvar):
+                res[names[v] + nm] = o[pos:pos + ln].copy()
+                pos += ln
+        res["E_spectrum3d"] = sum(res[k] for k in names[:3])
+        for ax in ("kx", "ky", "kz"):
+            res["E_" + ax] = sum(res[k + "_" + ax] for k in names[:3])
+        return res
+
+    def compute_1dspectra(self, energy_fft):
+        """fluidfft compute_1dspectra [EXT]: from an energy density array (kept for API parity; the
+        fused reduction above works on the fields themselves)."""
+        w = torch.full(self.shapeK_loc, 2.0, dtype=torch.float64, device=self.device)
+        w[..., 0] = 1.0
+        if self.nx % 2 == 0:
+            w[..., -1] = 1.0
+        E = energy_fft * w
+        e_kx = E.sum(dim=(0, 1)) / self.deltakx
+        iy = torch.round(self._k1d.abs() / self.deltaky).long()
+        iz = torch.round(self._k0d.abs() / self.deltakz).long()
+        e_ky = torch.zeros(self.ny // 2 + 1, dtype=torch.float64, device=self.device).index_add_(0, iy, E.sum(dim=(0, 2)))
+        e_kz = torch.zeros(self.nz // 2 + 1, dtype=torch.float64, device=self.device).index_add_(0, iz, E.sum(dim=(1, 2)))
+        return e_kx.cpu().numpy(), (e_ky / self.deltaky).cpu().numpy(), (e_kz / self.deltakz).cpu().numpy()
+
     @property
     def nk_spectra(self):
         return (

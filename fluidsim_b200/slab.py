@@ -419,6 +419,35 @@ class SlabSimul:
         self.dist.all_reduce(flag, op=self.dist.ReduceOp.MAX, group=self.group)
         return int(flag.item()) == 0
 
+    def compute_observables(self):
+        """Spatial means + 1-D / 3-D spectra of the velocity in one kernel pass per rank
+        (``b2_observables``) and one all-reduce (SUM); same dictionary as
+        ``OperatorsPseudoSpectral3D.compute_observables``."""
+        import math
+
+        from ._lib import call, lib, ptr, stream_ptr
+
+        po = self.params.oper
+        dks = [2 * math.pi / float(po.Lx), 2 * math.pi / float(po.Ly), 2 * math.pi / float(po.Lz)]
+        deltak = max(dks)
+        nks = int(math.sqrt((dks[0] * (self.nx // 2)) ** 2 + (dks[1] * (self.ny // 2)) ** 2
+                            + (dks[2] * (self.nz // 2)) ** 2) / deltak) + 2
+        n = int(lib.b2_observables_size(self.handle, 3, nks))
+        out = self.torch.empty(n, dtype=self.torch.float64, device=self.device)
+        call("b2_observables", self.handle, ptr(self.state_spect), 3, nks, deltak, ptr(out), stream_ptr())
+        self.dist.all_reduce(out, group=self.group)
+        o = out.cpu().numpy()
+        res = {"Ex": float(o[0]), "Ey": float(o[1]), "Ez": float(o[2]), "E": float(o[0] + o[1] + o[2]),
+               "epsK": float(o[4]), "epsK_hypo": float(o[5]), "epsK4": float(o[6]), "epsK8": float(o[7]),
+               "enstrophy": float(o[8])}
+        pos = 16
+        for nm, ln in (("", nks), ("_kx", self.nx // 2 + 1), ("_ky", self.ny // 2 + 1), ("_kz", self.nz // 2 + 1)):
+            for v in ("vx", "vy", "vz"):
+                res[v + nm] = o[pos:pos + ln].copy()
+                pos += ln
+        res["E_spectrum3d"] = res["vx"] + res["vy"] + res["vz"]
+        return res
+
     def compute_energy(self):
         """sum_wavenumbers(|v|^2)/2 over the velocity components, all-reduced."""
         from ._lib import call, ptr, stream_ptr

@@ -111,6 +111,18 @@ int b2_rk4_step3(b2_plan* p, double* S, const double* acc, const double* T, doub
 /* sum_wavenumbers(|f|^2) over nvar fields (r2c-aware weights), result written to *out_dev (device
  * double).  compute_energy_from_K = 0.5 * this. */
 int b2_sum_wavenumbers_abs2(b2_plan* p, const double* fields, int nvar, double* out_dev, void* stream);
+/* every reduction the reference's periodic outputs take from state_spect, in ONE pass: component
+ * energies, dissipation rates epsK / epsK_hypo / epsK4 / epsK8, enstrophy
+ * (solvers/ns3d/output/spatial_means.py:23-73), shell-binned 3-D spectra and 1-D spectra of every
+ * variable (solvers/ns3d/output/spectra.py:15-60; fluidfft compute_3dspectrum / compute_1dspectra).
+ * nks = oper.nk_spectra, deltak = oper.deltak.  out_dev (device doubles, b2_observables_size of
+ * them): [0..3] E per variable, [4] epsK, [5] epsK_hypo, [6] epsK4, [7] epsK8, [8] enstrophy,
+ * [9..15] reserved, then spec3d[nvar][nks], s_kx[nvar][nx/2+1], s_ky[nvar][ny/2+1],
+ * s_kz[nvar][nz/2+1].  Uses the viscosities of b2_set_physics.  Slab plans: local contribution,
+ * the caller all-reduces (SUM). */
+long long b2_observables_size(const b2_plan* p, int nvar, int nks);
+int b2_observables(b2_plan* p, const double* S, int nvar, int nks, double deltak, double* out_dev,
+                   void* stream);
 /* max |x| over n doubles -> *out_dev : _compute_time_increment_CLF_uxuyuz, base/time_stepping/base.py:320-339 */
 int b2_max_abs(const double* x, long long n, double* out_dev, void* stream);
 /* sum of all doubles (NaN check `np.isnan(np.sum(state_spect[0]))`, solvers/ns3d/time_stepping.py:19) */

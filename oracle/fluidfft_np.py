@@ -446,6 +446,28 @@ class OperatorsPseudoSpectral3D:
         return spectrum / self.deltak
 
 
+    def compute_1dspectra(self, energy_fft):
+        """E(kx), E(ky), E(kz) [EXT fluidfft, restated per SURVEY Appendix A]: r2c weights along kx,
+        +-ky and +-kz folded on |k| index, each divided by its own deltak so that
+        sum(E_ki) * deltaki = sum_wavenumbers(energy_fft)."""
+        w = np.full(self.shapeK_loc, 2.0)
+        w[..., 0] = 1.0
+        if self.nx % 2 == 0:
+            w[..., -1] = 1.0
+        E = energy_fft * w
+        nkz, nky = self.nz // 2 + 1, self.ny // 2 + 1
+        e_kx = E.sum(axis=(0, 1)) / self.deltakx
+        tmp_y = E.sum(axis=(0, 2))
+        iy = np.rint(np.abs(self.Ky[0, :, 0]) / self.deltaky).astype(int)
+        e_ky = np.zeros(nky)
+        np.add.at(e_ky, iy, tmp_y)
+        tmp_z = E.sum(axis=(1, 2))
+        iz = np.rint(np.abs(self.Kz[:, 0, 0]) / self.deltakz).astype(int)
+        e_kz = np.zeros(nkz)
+        np.add.at(e_kz, iz, tmp_z)
+        return e_kx, e_ky / self.deltaky, e_kz / self.deltakz
+
+
 # --------------------------------------------------------------------------- 2-D operators
 class OperatorsPseudoSpectral2D:
     """Restated fluidfft.fft2d.operators.OperatorsPseudoSpectral2D (sequential)."""

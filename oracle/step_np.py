@@ -393,6 +393,46 @@ class OracleSim:
         return self.oper.compute_3dspectrum(e)
 
     # ------------------------------------------------------------------ initial fields
+    def compute_spatial_means(self):
+        """The state reductions of SpatialMeansNS3D._save_one_time
+        (solvers/ns3d/output/spatial_means.py:23-43): E, Ex, Ey, Ez, epsK, epsK_hypo, epsK4, epsK8."""
+        oper = self.oper
+        s = np.array(self.state_spect)
+        nrj = [0.5 * np.abs(s[i]) ** 2 for i in range(3)]
+        energy_fft = nrj[0] + nrj[1] + nrj[2]
+        sw = oper.sum_wavenumbers
+        K2 = oper.K2
+        f_d = self.nu_2 * K2 if self.nu_2 > 0 else np.zeros_like(K2)
+        if self.nu_4 > 0:
+            f_d = f_d + self.nu_4 * K2**2
+        if self.nu_8 > 0:
+            f_d = f_d + self.nu_8 * K2**4
+        out = dict(Ex=sw(nrj[0]), Ey=sw(nrj[1]), Ez=sw(nrj[2]), epsK=sw(f_d * 2 * energy_fft))
+        out["E"] = out["Ex"] + out["Ey"] + out["Ez"]
+        if self.nu_m4 != 0.0:
+            K2n = K2.copy()
+            K2n[0, 0, 0] = K2[0, 0, 1]
+            out["epsK_hypo"] = sw(self.nu_m4 / K2n**2 * 2 * energy_fft)
+        else:
+            out["epsK_hypo"] = 0.0
+        out["epsK4"] = sw(self.nu_4 * K2**2 * 2 * energy_fft) if self.nu_4 > 0 else 0.0
+        out["epsK8"] = sw(self.nu_8 * K2**4 * 2 * energy_fft) if self.nu_8 > 0 else 0.0
+        return out
+
+    def compute_spectra(self):
+        """SpectraNS3D.compute (solvers/ns3d/output/spectra.py:15-60): per-component 1-D and 3-D spectra."""
+        oper = self.oper
+        s = np.array(self.state_spect)
+        out = {}
+        for i, key in enumerate(("vx", "vy", "vz")):
+            nrj = 0.5 * np.abs(s[i]) ** 2
+            out[key + "_kx"], out[key + "_ky"], out[key + "_kz"] = oper.compute_1dspectra(nrj)
+            out[key] = oper.compute_3dspectrum(nrj)
+        out["E"] = out["vx"] + out["vy"] + out["vz"]
+        for ax in ("kx", "ky", "kz"):
+            out["E_" + ax] = out["vx_" + ax] + out["vy_" + ax] + out["vz_" + ax]
+        return out
+
     def init_noise(self, velo_max=1.0, length=None, seed=42):
         """ns3d/init_fields.py:110-196 ; ns2d/init_fields.py:57-108."""
         oper = self.oper

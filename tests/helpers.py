@@ -8,8 +8,17 @@ import numpy as np
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def golden_cases():
+def all_golden_cases():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_cases():
+    """Unforced fixtures (the forced ones need a forcing object: ``forced_golden_cases``)."""
+    return [n for n in all_golden_cases() if not n.endswith("_forced")]
+
+
+def forced_golden_cases():
+    return [n for n in all_golden_cases() if n.endswith("_forced")]
 
 
 def load_golden(name):

@@ -3,11 +3,11 @@ against the reference's own modules executed through ``oracle.refshim``."""
 import numpy as np
 import pytest
 
-from helpers import golden_cases, load_golden, make_oracle, rel_err
+from helpers import all_golden_cases, golden_cases, load_golden, make_oracle, rel_err
 from oracle import refshim, step_np
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", all_golden_cases())
 def test_oracle_matches_golden(name):
     meta, z = load_golden(name)
     o = make_oracle(meta)
@@ -122,3 +122,22 @@ def test_forced_goldens_differ_from_the_unforced_run():
         assert np.array_equal(zf["state0"], zp["state0"])
         assert np.abs(zf["forcing"]).max() > 0
         assert rel_err(zf["state1"], zp["state1"]) > 1e-4
+
+
+def test_oracle_spectra_and_means_are_consistent():
+    """1-D / 3-D spectra [EXT restatement] integrate to the energy; means add up; the dissipation of a
+    nu_2 run equals 2 nu_2 Z for a solenoidal field (Z = enstrophy)."""
+    o = step_np.OracleSim("ns3d", 16, 12, 8, nu_2=1e-2, nu_m4=1e-3, Lx=6.0)
+    o.init_noise()
+    m = o.compute_spatial_means()
+    sp = o.compute_spectra()
+    op = o.oper
+    assert abs(m["E"] - o.compute_energy()) < 1e-15
+    for key, dk in (("E", op.deltak), ("E_kx", op.deltakx), ("E_ky", op.deltaky), ("E_kz", op.deltakz)):
+        assert abs(sp[key].sum() * dk - m["E"]) < 1e-14 * m["E"]
+    assert sp["vx_kx"].shape == (16 // 2 + 1,) and sp["vx_ky"].shape == (12 // 2 + 1,)
+    assert sp["vx_kz"].shape == (8 // 2 + 1,)
+    o2 = step_np.OracleSim("ns3d", 16, 16, 16, nu_2=1e-2)
+    o2.init_noise()
+    m2 = o2.compute_spatial_means()
+    assert abs(m2["epsK"] - 2 * 1e-2 * o2.compute_enstrophy()) < 1e-12 * m2["epsK"]

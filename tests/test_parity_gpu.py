@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import scipy.fft as sfft
 
-from helpers import golden_cases, load_golden, make_gpu_sim, make_oracle, rel_err, set_state
+from helpers import forced_golden_cases, golden_cases, load_golden, make_gpu_sim, make_oracle, rel_err, set_state
 
 pytestmark = pytest.mark.gpu
 
@@ -200,11 +200,36 @@ def test_config1_ns2d_256_noise_rk4_100_steps():
     assert abs(z_gpu - z_o) < TOL_OBS * z_o
 
 
-def test_config2_ns3d_128_taylor_green_rk4():
-    """BASELINE config 2: ns3d 128^3 Taylor-Green RK4 (nu_2 = 1/1600, dt = 1e-2): per-step state
-    parity, then energy / spectrum / spatial means."""
+def _check_observables(sim, o, tol=TOL_OBS):
+    """GPU one-pass reduction (b2_observables) against the oracle's restatement of the reference
+    outputs: spatial means (E, Ex, Ey, Ez, epsK...), 3-D and 1-D spectra of every component."""
+    sim._ensure_fused_buffers()  # pushes the viscosities
+    obs = sim.oper.compute_observables(sim.state.state_spect.tensor[:3])
+    means = o.compute_spatial_means()
+    for key in ("E", "Ex", "Ey", "Ez", "epsK", "epsK_hypo", "epsK4", "epsK8"):
+        assert abs(obs[key] - means[key]) <= tol * max(abs(means[key]), 1e-30) + 1e-300, key
+    assert abs(obs["enstrophy"] - o.compute_enstrophy()) <= tol * o.compute_enstrophy()
+    spec = o.compute_spectra()
+    for comp in ("vx", "vy", "vz"):
+        scale = max(spec["E"].max(), 1e-300)
+        assert np.abs(obs[comp] - spec[comp]).max() <= tol * scale, comp
+        for ax in ("kx", "ky", "kz"):
+            ref = spec[f"{comp}_{ax}"]
+            assert obs[f"{comp}_{ax}"].shape == ref.shape
+            assert np.abs(obs[f"{comp}_{ax}"] - ref).max() <= tol * max(spec["E_" + ax].max(), 1e-300), (comp, ax)
+    # spectra integrate to the energy
+    oper = sim.oper
+    assert abs(obs["E_spectrum3d"].sum() * oper.deltak - obs["E"]) < 1e-12 * obs["E"]
+    assert abs(obs["E_kx"].sum() * oper.deltakx - obs["E"]) < 1e-12 * obs["E"]
+    assert abs(obs["E_kz"].sum() * oper.deltakz - obs["E"]) < 1e-12 * obs["E"]
+
+
+def test_config2_ns3d_128_taylor_green_rk4_100_steps():
+    """BASELINE config 2: ns3d 128^3 Taylor-Green RK4 (nu_2 = 1/1600, dt = 1e-2), the full 100 steps of
+    the north-star: state within 1e-10 per step, then energy, enstrophy, 3-D AND 1-D spectra and the
+    spatial means within 1e-8 (the oracle needs ~1 s per step on the box's host cores)."""
     meta = dict(solver="ns3d", shape=(128, 128, 128), params=dict(nu_2=1 / 1600.0, deltat0=1e-2))
-    nsteps = 20  # the oracle needs ~1 s per step on the box's host cores
+    nsteps = 100
     o, sim, worst = _run_both(meta, nsteps, "init_taylor_green")
     assert worst < 1e-10
     e_o = o.compute_energy()
@@ -214,6 +239,9 @@ def test_config2_ns3d_128_taylor_green_rk4():
     spec_gpu = sim.oper.compute_3dspectrum(e_fft)
     spec_o = o.compute_spectrum3d()
     assert np.abs(spec_gpu - spec_o).max() < TOL_OBS * spec_o.max()
+    _check_observables(sim, o)
+    # Taylor-Green anchor: E(0) = 1/8 and the energy has decayed (doc/examples taylor-green)
+    assert 0.11 < e_o < 0.125
     # spatial means of the physical fields (vx^2 ...), from the lazily computed state_phys
     phys = sim.state.state_phys.numpy()
     for i in range(3):
@@ -221,11 +249,36 @@ def test_config2_ns3d_128_taylor_green_rk4():
         assert abs(float(np.mean(phys[i] ** 2)) - m_o) < TOL_OBS * max(m_o, 1e-3)
 
 
-def test_ns3d_strat_64_noise_rk4():
-    meta = dict(solver="ns3d.strat", shape=(64, 64, 64), params=dict(nu_8=1e-10, deltat0=5e-3, N=1.0))
+@pytest.mark.parametrize("name", ["ns3d_16x12x8_rk4_odd", "ns3d_32x16x8_rk2_f", "ns3d_20x15x10_rk4_spherical"])
+def test_observables_kernel_matches_oracle_small_and_odd_grids(name):
+    """b2_observables on anisotropic / odd grids and non-unit boxes (bin folding, r2c weights with an
+    odd nx, hypo-viscous dissipation) against the oracle after the golden's steps."""
+    meta, z = load_golden(name)
+    o = make_oracle(meta)
+    o.set_state_spect(z["stateN"])
+    sim = make_gpu_sim(meta, fused=None, mask=z["mask"])
+    set_state(sim, z["stateN"])
+    import ctypes as C
+
+    from fluidsim_b200._lib import SOLVER_IDS, call, ptr
+
+    call("b2_set_physics", sim.oper.plan.handle, SOLVER_IDS["ns3d"], *sim._physics_args(), ptr(sim.oper.where_dealiased))
+    obs = sim.oper.compute_observables(sim.state.state_spect.tensor[:3])
+    means = o.compute_spatial_means()
+    for key in ("E", "Ex", "Ey", "Ez", "epsK", "epsK_hypo", "epsK4", "epsK8"):
+        assert abs(obs[key] - means[key]) <= 1e-12 * max(abs(means[key]), 1e-30) + 1e-300, key
+    spec = o.compute_spectra()
+    for key in ("vx", "vy", "vz", "vx_kx", "vy_ky", "vz_kz", "vx_kz", "vz_ky"):
+        assert np.abs(obs[key] - spec[key]).max() <= 1e-12 * spec["E"].max(), key
+
+
+def test_ns3d_strat_128_noise_rk4():
+    """ns3d.strat (config 4's solver) at 128^3 against the oracle: 10 RK4 steps with N = 1."""
+    meta = dict(solver="ns3d.strat", shape=(128, 128, 128), params=dict(nu_8=1e-10, deltat0=5e-3, N=1.0))
     o, sim, worst = _run_both(meta, 10, "init_noise")
     assert worst < 1e-10
     assert abs(sim.state.compute_energy_spect() - o.compute_energy()) < TOL_OBS * o.compute_energy()
+    _check_observables(sim, o)
 
 
 # ------------------------------------------------------------------ invariants at larger sizes
@@ -520,7 +573,7 @@ def _forced_sim(meta, z, fused):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ns3d_16x16x16_rk4_forced", "strat_16x16x16_rk4_forced", "ns2d_32x32_rk4_forced"])
+@pytest.mark.parametrize("name", forced_golden_cases())
 @pytest.mark.parametrize("fused", [False, True])
 def test_forced_step_matches_reference_golden(name, fused):
     """`tendencies_fft += forcing.get_forcing()` (/root/reference/fluidsim/solvers/ns3d/solver.py:243-244,

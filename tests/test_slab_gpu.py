@@ -62,6 +62,16 @@ def _worker(rank, world, port, name, nchunks, dist_kind, lean, q):
             sim.one_time_step()
         e_n = rel_err(sim.gather_state(), z["stateN"])
         e_en = abs(sim.compute_energy() - float(z["energyN"])) / float(z["energyN"])
+        # one-pass observables on the slab layout (local kernel + all-reduce) against the oracle
+        from helpers import make_oracle
+
+        o = make_oracle(meta)
+        o.set_state_spect(z["stateN"])
+        obs, spec, means = sim.compute_observables(), o.compute_spectra(), o.compute_spatial_means()
+        e_en = max(e_en, abs(obs["E"] - means["E"]) / means["E"], abs(obs["epsK"] - means["epsK"]) / max(means["epsK"], 1e-300),
+                   float(np.abs(obs["E_spectrum3d"] - spec["E"]).max() / spec["E"].max()),
+                   float(np.abs(obs["vy_ky"] - spec["vy_ky"]).max() / spec["E_ky"].max()),
+                   float(np.abs(obs["vz_kz"] - spec["vz_kz"]).max() / spec["E_kz"].max()))
         q.put((rank, e_t, e_1, e_n, e_en))
     finally:
         dist.destroy_process_group()
