@@ -97,3 +97,32 @@ def test_default_params_have_reference_names():
     assert p2.oper.Lx == 8 and hasattr(p2, "beta")
     with pytest.raises(ValueError):
         create_default_params("sw1l")
+
+
+def test_pyproject_entry_points_resolve():
+    """Every entry point declared in pyproject.toml (fluidfft.plugins, fluidsim.solvers.*) names an
+    importable module with the attribute the reference's loaders look up: ``FFTclass`` for fluidfft
+    plugins (operators3d.py:229 through fluidfft.import_fft_class), ``Simul`` for solver modules
+    (lib/fluidsim_core/loader.py:17-74)."""
+    import importlib
+    import os
+    import tomllib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "pyproject.toml"), "rb") as f:
+        eps = tomllib.load(f)["project"]["entry-points"]
+    assert set(eps) == {"fluidfft.plugins", "fluidsim.solvers.ns3d", "fluidsim.solvers.ns2d"}
+    for name, target in eps["fluidfft.plugins"].items():
+        mod = importlib.import_module(target)
+        cls = mod.FFTclass
+        layout = "get_dimX_K" if name.startswith("fft3d") else "get_is_transposed"  # 3-D / 2-D plugins
+        for meth in ("fft_as_arg", "ifft_as_arg", "ifft_as_arg_destroy", "fft", "ifft", "get_shapeX_loc",
+                     "get_shapeK_loc", "get_shapeK_seq", layout, "get_seq_indices_first_K",
+                     "get_k_adim_loc", "sum_wavenumbers", "create_arrayX", "create_arrayK"):
+            assert hasattr(cls, meth), (name, meth)
+    for group in ("fluidsim.solvers.ns3d", "fluidsim.solvers.ns2d"):
+        for name, target in eps[group].items():
+            Simul = importlib.import_module(target).Simul
+            p = Simul.create_default_params()
+            assert p.time_stepping.type_time_scheme == "RK4"
+            assert hasattr(Simul, "InfoSolver") and hasattr(Simul, "tendencies_nonlin")

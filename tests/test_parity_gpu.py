@@ -641,3 +641,34 @@ def test_normalised_forcing_injects_the_prescribed_rate(ftype):
         div = oper.divfft_from_vecfft(f[0], f[1], f[2])
         assert float(div.abs().max()) < 1e-12
     assert sim.state.compute_energy_spect() > e0
+
+
+@pytest.mark.gpu
+def test_fluidfft_plugin_contract_numpy_operators_on_the_gpu_fft():
+    """FFT-only drop-in: the numpy operator layer and the reference-shaped
+    RK4 step of the oracle driven by ``FFT3DWithB200`` as their fluidfft plugin object, numpy arrays in
+    and out (``fft_as_arg`` / ``ifft_as_arg`` / ``ifft_as_arg_destroy`` / shapes / k_adim /
+    sum_wavenumbers) -- must equal the pure-numpy run."""
+    from fluidsim_b200.fft3d_with_b200 import FFTclass
+    from oracle import step_np
+
+    nx, ny, nz = 32, 16, 8
+    kw = dict(nu_2=1e-2, deltat0=1e-2, Lx=6.0, Ly=4.0, Lz=3.0)
+    ref = step_np.OracleSim("ns3d", nx, ny, nz, **kw)
+    ref.init_noise()
+    o = step_np.OracleSim("ns3d", nx, ny, nz, **kw)
+    plugin = FFTclass(nz, ny, nx)
+    assert plugin.get_shapeK_seq() == ref.oper.shapeK_seq and plugin.get_dimX_K() == (0, 1, 2)
+    mask = o.oper.where_dealiased.copy()
+    o.oper.__init__(nx, ny, nz, kw["Lx"], kw["Ly"], kw["Lz"], fft=plugin, coef_dealiasing=2.0 / 3)
+    o.oper.Lx, o.oper.Ly, o.oper.Lz = kw["Lx"], kw["Ly"], kw["Lz"]
+    o.oper.where_dealiased = mask
+    assert o.oper.type_fft == "fluidsim_b200.fft"
+    o.set_state_spect(np.array(ref.state_spect))
+    t_ref, t_gpu = np.array(ref.tendencies_nonlin()), np.array(o.tendencies_nonlin())
+    assert rel_err(t_gpu, t_ref) < 1e-12
+    for _ in range(3):
+        ref.one_time_step()
+        o.one_time_step()
+    assert rel_err(np.array(o.state_spect), np.array(ref.state_spect)) < 1e-11
+    assert abs(o.compute_energy() - ref.compute_energy()) < 1e-12 * ref.compute_energy()
