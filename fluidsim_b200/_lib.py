@@ -90,6 +90,12 @@ SIGNATURES = {
     "b2_slab_phase_a": [_p, _p, _i, _p],
     "b2_slab_phase_b": [_p, _p],
     "b2_slab_phase_c": [_p, _i, _i, _d, _p, _p, _p, _p],
+    "b2_nccl_unique_id": [_p],
+    "b2_slab_comm_init": [_p, _p],
+    "b2_slab_comm_destroy": [_p],
+    "b2_slab_tendencies": [_p, _p, _p, _p],
+    "b2_slab_time_step": [_p, _i, _d, _p, _p],
+    "b2_slab_time_step_cfl": [_p, _i, _d, _d, _p, _p, _p, _p],
     "b2_profile_enable": [_i],
     "b2_profile_reset": [],
     "b2_profile_get": [C.POINTER(_d), C.POINTER(_ll), _i],

@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <vector>
 
@@ -182,8 +184,10 @@ extern "C" int b2_plan_create_slab(b2_plan** out, int nz, int ny, int nx, double
     return 0;
 }
 
+extern "C" int b2_slab_comm_destroy(b2_plan* p);
 extern "C" int b2_plan_destroy(b2_plan* p) {
     if (!p) return 0;
+    b2_slab_comm_destroy(p);
     if (p->streams_ready) {
         cudaStreamDestroy(p->sy1); cudaStreamDestroy(p->sx); cudaStreamDestroy(p->sy2);
         cudaEventDestroy(p->ev_begin); cudaEventDestroy(p->ev_end);
@@ -1777,4 +1781,287 @@ extern "C" int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, con
     slab_counts(p, &nin, &nout);
     if ((e = b2_slab_zfwd(p, 0, nout, stream))) return e;
     return b2_slab_rk(p, scheme, stage, dt, S_in, S_, T_out, stream);
+}
+
+// ------------------------------------------------------------------------------- native collectives
+// The two global transposes of every 3-D FFT as grouped ncclSend / ncclRecv issued by the library
+// itself (the communicator belongs to the plan), so that a host in any
+// language drives the multi-GPU path through this C ABI alone: one call per time step.  NCCL is
+// bound at run time (dlopen of the libnccl.so.2 already loaded by the host process, e.g. PyTorch's),
+// so the library neither links against it nor needs it for single-GPU use.
+// Replaces: the MPI all-to-alls inside fluidfft's fft3d.mpi_with_fftwmpi3d transforms and the
+// allreduce of _compute_time_increment_CLF_uxuyuz (/root/reference/fluidsim/base/time_stepping/base.py:320-354).
+typedef struct { char internal[128]; } b2_nccl_uid;
+struct NcclApi {
+    void* handle;
+    int (*GetUniqueId)(b2_nccl_uid*);
+    int (*CommInitRank)(void**, int, b2_nccl_uid, int);
+    int (*CommDestroy)(void*);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t);
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    const char* (*GetErrorString)(int);
+};
+enum { B2_NCCL_FLOAT64 = 8, B2_NCCL_SUM = 0, B2_NCCL_MAX = 2 };  // ncclDouble, ncclSum, ncclMax (nccl.h)
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    static int state = 0;  // 0 untried, 1 ok, -1 unavailable
+    if (state == 0) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        state = -1;
+        if (h) {
+            api.handle = h;
+#define B2_SYM(field, name) *(void**)(&api.field) = dlsym(h, name)
+            B2_SYM(GetUniqueId, "ncclGetUniqueId");
+            B2_SYM(CommInitRank, "ncclCommInitRank");
+            B2_SYM(CommDestroy, "ncclCommDestroy");
+            B2_SYM(GroupStart, "ncclGroupStart");
+            B2_SYM(GroupEnd, "ncclGroupEnd");
+            B2_SYM(Send, "ncclSend");
+            B2_SYM(Recv, "ncclRecv");
+            B2_SYM(AllReduce, "ncclAllReduce");
+            B2_SYM(GetErrorString, "ncclGetErrorString");
+#undef B2_SYM
+            if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd &&
+                api.Send && api.Recv && api.AllReduce && api.GetErrorString)
+                state = 1;
+        }
+    }
+    return state == 1 ? &api : nullptr;
+}
+#define NCCL_TRY(expr)                                                                       \
+    do {                                                                                     \
+        int _r = (expr);                                                                     \
+        if (_r != 0) return b2i_set_error(#expr ": %s", nccl_api()->GetErrorString(_r));     \
+    } while (0)
+
+/* 128-byte NCCL unique id (rank 0 creates it, the host broadcasts it to the other ranks) */
+extern "C" int b2_nccl_unique_id(void* out128) {
+    NcclApi* n = nccl_api();
+    if (!n) return b2i_set_error("b2_nccl_unique_id: libnccl.so.2 not found");
+    NCCL_TRY(n->GetUniqueId((b2_nccl_uid*)out128));
+    return 0;
+}
+extern "C" int b2_slab_comm_init(b2_plan* p, const void* uid128) {
+    if (!p->slab) return b2i_set_error("b2_slab_comm_init: not a slab plan");
+    NcclApi* n = nccl_api();
+    if (!n) return b2i_set_error("b2_slab_comm_init: libnccl.so.2 not found");
+    if (p->comm_ready) return 0;
+    b2_nccl_uid uid;
+    memcpy(&uid, uid128, sizeof(uid));
+    NCCL_TRY(n->CommInitRank(&p->nccl_comm, p->nranks, uid, p->rank));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->comm_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 128; ++i) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_comm[i], cudaEventDisableTiming));
+    p->comm_ready = true;
+    return 0;
+}
+extern "C" int b2_slab_comm_destroy(b2_plan* p) {
+    if (!p || !p->comm_ready) return 0;
+    cudaStreamSynchronize(p->comm_stream);
+    nccl_api()->CommDestroy(p->nccl_comm);
+    cudaStreamDestroy(p->comm_stream);
+    for (int i = 0; i < 128; ++i) cudaEventDestroy(p->ev_comm[i]);
+    p->comm_ready = false;
+    return 0;
+}
+
+struct SlabExchange {
+    long long mine;              // complex elements sent to (K side) / received from every peer
+    long long theirs[8];         // complex elements of peer r on the z-slab side (<= 8 ranks, one node)
+    long long theirs_off[8];
+    long long cs_a, cs_b;        // chunk strides of xa / xb
+};
+static SlabExchange slab_exchange(const b2_plan* p) {
+    SlabExchange ex;
+    const long long pitch = p->prune ? p->keepx : p->nk;
+    const long long row = (long long)(p->nzl / p->slab_nc) * pitch;
+    long long tot = 0;
+    for (int r = 0; r < p->nranks; ++r) {
+        int lo, hi;
+        b2i_slab_local_band(p, r, &lo, &hi);
+        const long long nkl = p->nyl - (hi - lo);
+        ex.theirs[r] = nkl * row;
+        ex.theirs_off[r] = tot;
+        tot += ex.theirs[r];
+        if (r == p->rank) ex.mine = nkl * row;
+    }
+    ex.cs_a = (long long)p->gy * row;
+    ex.cs_b = tot;
+    return ex;
+}
+// inverse direction: xa (K side, equal blocks per peer) -> xb (z-slab side, rows grouped by owner);
+// forward: the opposite.  One grouped send/recv per (field, chunk) on the plan's comm stream.
+static int slab_a2a(b2_plan* p, const SlabExchange& ex, int f, int c, bool inverse) {
+    NcclApi* n = nccl_api();
+    cplx* a = p->xa + (long long)f * p->xa_stride() + (long long)c * ex.cs_a;
+    cplx* b = p->xb + (long long)f * p->xb_stride() + (long long)c * ex.cs_b;
+    NCCL_TRY(n->GroupStart());
+    for (int r = 0; r < p->nranks; ++r) {
+        cplx* ablk = a + (long long)r * ex.mine;
+        cplx* bblk = b + ex.theirs_off[r];
+        if (inverse) {
+            if (ex.mine > 0) NCCL_TRY(n->Send(ablk, (size_t)ex.mine * 2, B2_NCCL_FLOAT64, r, p->nccl_comm, p->comm_stream));
+            if (ex.theirs[r] > 0) NCCL_TRY(n->Recv(bblk, (size_t)ex.theirs[r] * 2, B2_NCCL_FLOAT64, r, p->nccl_comm, p->comm_stream));
+        } else {
+            if (ex.theirs[r] > 0) NCCL_TRY(n->Send(bblk, (size_t)ex.theirs[r] * 2, B2_NCCL_FLOAT64, r, p->nccl_comm, p->comm_stream));
+            if (ex.mine > 0) NCCL_TRY(n->Recv(ablk, (size_t)ex.mine * 2, B2_NCCL_FLOAT64, r, p->nccl_comm, p->comm_stream));
+        }
+    }
+    NCCL_TRY(n->GroupEnd());
+    b2i_count_launch();
+    return 0;
+}
+
+// One evaluation of the nonlinear term + RK epilogue with the pipelined schedule of
+// fluidsim_b200/slab.py::_run_stage: the all-to-all of (field f, chunk c) runs on the comm stream
+// while the compute stream does the z pass of the next field / the y and x passes of the previous
+// chunk.  vmax_dev != NULL: max |v| side output of the x passes (stage 0 of a CFL step).
+static int slab_stage_native(b2_plan* p, int scheme, int stage, double dt, const double* dt_dev, const double* S_in,
+                             double* S_, double* T_out, bool need_curl, double* vmax_dev, cudaStream_t s) {
+    int e, nin, nout;
+    if ((e = slab_ready(p))) return e;
+    if (!p->comm_ready) return b2i_set_error("b2_slab_comm_init has not been called");
+    slab_counts(p, &nin, &nout);
+    const int nc = p->slab_nc;
+    if (nin * nc * 2 + nout * nc * 2 > 128) return b2i_set_error("too many (field, chunk) pieces");
+    const SlabExchange ex = slab_exchange(p);
+    cudaStream_t cs = p->comm_stream;
+    int order[8], no = 0;
+    if (need_curl) {
+        for (int f = 0; f < 3; ++f) order[no++] = f;
+        for (int f = 6; f < nin; ++f) order[no++] = f;
+        for (int f = 3; f < 6; ++f) order[no++] = f;
+    } else {
+        for (int f = 0; f < nin; ++f) order[no++] = f;
+    }
+    cudaEvent_t* ev = p->ev_comm;
+    auto evA = [&](int f) { return ev[f]; };                              // zinv(f) done (compute)
+    auto evI = [&](int f, int c) { return ev[8 + f * nc + c]; };          // a2a_inv(f, c) done (comm)
+    auto evY = [&](int f, int c) { return ev[8 + (nin + f) * nc + c]; };  // yfwd(f, c) done (compute)
+    auto evF = [&](int f, int c) { return ev[8 + (nin + nout + f) * nc + c]; };  // a2a_fwd done (comm)
+    if (8 + (nin + 2 * nout) * nc > 128) return b2i_set_error("too many (field, chunk) pieces");
+    bool curl_done = !need_curl;
+    for (int k = 0; k < no; ++k) {
+        const int f = order[k];
+        if (!curl_done && f >= 3 && f < 6) {
+            if ((e = b2_slab_curl(p, S_in, s))) return e;
+            curl_done = true;
+        }
+        if ((e = b2_slab_zinv(p, S_in, f, f + 1, s))) return e;
+        CUDA_TRY(cudaEventRecord(evA(f), s));
+        CUDA_TRY(cudaStreamWaitEvent(cs, evA(f), 0));
+        if ((e = slab_a2a(p, ex, f, 0, true))) return e;
+        CUDA_TRY(cudaEventRecord(evI(f, 0), cs));
+    }
+    for (int c = 1; c < nc; ++c)
+        for (int k = 0; k < no; ++k) {
+            const int f = order[k];
+            if ((e = slab_a2a(p, ex, f, c, true))) return e;
+            CUDA_TRY(cudaEventRecord(evI(f, c), cs));
+        }
+    for (int c = 0; c < nc; ++c) {
+        for (int k = 0; k < no; ++k) {
+            const int f = order[k];
+            CUDA_TRY(cudaStreamWaitEvent(s, evI(f, c), 0));
+            if ((e = b2_slab_yinv(p, f, f + 1, c, s))) return e;
+        }
+        {
+            const long long fs_unused = 0; (void)fs_unused;
+            cplx* XW[8];
+            for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+            const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
+            const int pitch = p->prune ? p->keepx : p->nk;
+            const long long lines_c = (long long)p->gy * (p->nzl / nc);
+            ProfScope ps(PC_X_FUSED, s);
+            if ((e = b2i_xpass_fused(p, XW, lines_c, scale, pitch, pitch, lines_c * c, s, vmax_dev))) return e;
+        }
+        for (int f = 0; f < nout; ++f) {
+            if ((e = b2_slab_yfwd(p, f, f + 1, c, s))) return e;
+            CUDA_TRY(cudaEventRecord(evY(f, c), s));
+            CUDA_TRY(cudaStreamWaitEvent(cs, evY(f, c), 0));
+            if ((e = slab_a2a(p, ex, f, c, false))) return e;
+            CUDA_TRY(cudaEventRecord(evF(f, c), cs));
+        }
+    }
+    if (vmax_dev) {
+        // CFL: global max |v_i| (allreduce MAX of three doubles on the comm stream, after the x passes)
+        NcclApi* n = nccl_api();
+        CUDA_TRY(cudaEventRecord(evA(7), s));
+        CUDA_TRY(cudaStreamWaitEvent(cs, evA(7), 0));
+        NCCL_TRY(n->AllReduce(vmax_dev, vmax_dev, 3, B2_NCCL_FLOAT64, B2_NCCL_MAX, p->nccl_comm, cs));
+        CUDA_TRY(cudaEventRecord(evA(7), cs));
+    }
+    for (int f = 0; f < nout; ++f) {
+        for (int c = 0; c < nc; ++c) CUDA_TRY(cudaStreamWaitEvent(s, evF(f, c), 0));
+        if ((e = b2_slab_zfwd(p, f, f + 1, s))) return e;
+    }
+    if (vmax_dev) CUDA_TRY(cudaStreamWaitEvent(s, evA(7), 0));
+    (void)dt_dev;
+    return 0;  // the caller launches the epilogue (it may first need the CFL kernel)
+}
+
+static int slab_rk_native(b2_plan* p, int scheme, int stage, double dt, const double* dt_dev, const double* S_in,
+                          double* S_, double* T_out, cudaStream_t s) {
+    int mode;
+    if (stage < 0) mode = M_TEND;
+    else if (scheme == B2_SCHEME_RK4 && stage < 4) mode = M_RK4_0 + stage;
+    else if (scheme == B2_SCHEME_RK2 && stage < 2) mode = M_RK2_0 + stage;
+    else return b2i_set_error("bad scheme/stage %d/%d", scheme, stage);
+    if (mode != M_TEND && (!p->acc || !p->stage)) return b2i_set_error("b2_set_buffers: acc/stage missing");
+    RKArgs a = rk_args(p, (const cplx*)S_in, (cplx*)S_, dt);
+    a.dt_ptr = dt_dev;
+    a.Tout = (cplx*)T_out;
+    return launch_rk_stage(p, mode, a, s);
+}
+
+/* N(S_in) on a slab plan with the library's own all-to-alls (stage < 0 semantics of b2_slab_rk) */
+extern "C" int b2_slab_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int e;
+    if ((e = slab_stage_native(p, B2_SCHEME_RK4, -1, 0.0, nullptr, S_in, nullptr, T_out, true, nullptr, s))) return e;
+    return slab_rk_native(p, B2_SCHEME_RK4, -1, 0.0, nullptr, S_in, nullptr, T_out, s);
+}
+
+/* one full RK2 / RK4 step on a slab plan: FFT passes, all-to-alls (NCCL, overlapped), epilogues */
+extern "C" int b2_slab_time_step(b2_plan* p, int scheme, double dt, double* S_, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scheme != B2_SCHEME_RK4 && scheme != B2_SCHEME_RK2)
+        return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
+    const int nst = scheme == B2_SCHEME_RK4 ? 4 : 2;
+    int e;
+    for (int st = 0; st < nst; ++st) {
+        const double* Sin = st == 0 ? S_ : (const double*)p->stage;
+        if ((e = slab_stage_native(p, scheme, st, dt, nullptr, Sin, S_, nullptr, st == 0, nullptr, s))) return e;
+        if ((e = slab_rk_native(p, scheme, st, dt, nullptr, Sin, S_, nullptr, s))) return e;
+    }
+    return 0;
+}
+
+/* the same with the CFL time increment decided on the device from the GLOBAL max |v_i|
+ * (base/time_stepping/base.py:320-354 with its MPI allreduce); see b2_time_step_cfl */
+extern "C" int b2_slab_time_step_cfl(b2_plan* p, int scheme, double cfl, double deltat_max, double* dt_dev,
+                                     double* vmax_dev, double* S_, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (scheme != B2_SCHEME_RK4 && scheme != B2_SCHEME_RK2)
+        return b2i_set_error("Problem name time_scheme (scheme id %d)", scheme);
+    if (!dt_dev || !vmax_dev) return b2i_set_error("b2_slab_time_step_cfl: dt_dev / vmax_dev missing");
+    const int nst = scheme == B2_SCHEME_RK4 ? 4 : 2;
+    int e;
+    for (int st = 0; st < nst; ++st) {
+        const double* Sin = st == 0 ? S_ : (const double*)p->stage;
+        if ((e = slab_stage_native(p, scheme, st, 0.0, dt_dev, Sin, S_, nullptr, st == 0, st == 0 ? vmax_dev : nullptr, s)))
+            return e;
+        if (st == 0) {
+            // slab plans store (L0, L1, L2) = (Ly, Lz, Lx) and n1 = nz
+            const double idx = p->n2 / p->L2, idy = p->gy / p->L0, idz = p->n1 / p->L1;
+            cfl_dt_kernel<<<1, 1, 0, s>>>(vmax_dev, idx, idy, idz, cfl, deltat_max, dt_dev);
+            B2_LAUNCH_CHECK("cfl_dt_kernel");
+        }
+        if ((e = slab_rk_native(p, scheme, st, 0.0, dt_dev, Sin, S_, nullptr, s))) return e;
+    }
+    return 0;
 }

@@ -46,6 +46,12 @@ struct b2_plan {
     const long long* force_idx;
     const cplx* force_val;
     int force_nvar;
+    // native collectives (b2_slab_comm_init): NCCL communicator owned by the plan, its stream and the
+    // events that order the per-(field, chunk) all-to-alls against the FFT passes
+    void* nccl_comm;
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_comm[128];
+    bool comm_ready;
     long long xa_fs, xb_fs;  // elements between consecutive fields of xa / xb (0: fsize())
     // memory-lean buffers (b2_set_aliasing, ns3d): the raw transform outputs live in `stage`
     // (the epilogue rewrites them in place into the next stage input), `work` holds only omega (3 fields)

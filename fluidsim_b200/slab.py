@@ -159,6 +159,7 @@ class SlabSimul:
         self._scalar = torch.zeros(1, dtype=torch.float64, device=self.device)
         # dealias-pruned exchange (set up by set_mask...; used once the state is known dealiased)
         self.use_pruning = True
+        self.use_cfl = bool(getattr(params.time_stepping, "USE_CFL", False))
         self.pipelined = True  # overlap the per-(field, chunk) all-to-alls with the FFT passes
         # z chunks of the exchange layout (pipelining granularity)
         import os
@@ -170,6 +171,29 @@ class SlabSimul:
         self._state_dealiased = False
         self._prune = None
         self._push()
+        # native collectives: the all-to-alls are issued by the library itself (NCCL communicator owned
+        # by the plan, one C call per time step).  B2_SLAB_NATIVE=0 keeps the torch.distributed
+        # all_to_all_single orchestration below (also what the gloo CPU tests exercise).
+        self.native = False
+        if os.environ.get("B2_SLAB_NATIVE", "1") not in ("0", "") and dist.get_backend(group) == "nccl":
+            self._init_native_comm()
+        self._dt_dev = self._vmax_dev = None
+
+    def _init_native_comm(self):
+        from ._lib import call, ptr
+
+        tr = self.torch
+        uid = tr.zeros(128, dtype=tr.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            call("b2_nccl_unique_id", buf)
+            uid = tr.frombuffer(bytearray(buf.raw), dtype=tr.uint8).clone()
+        uid = uid.to(self.device)
+        src = self.dist.get_global_rank(self.group, 0) if self.group is not None else 0
+        self.dist.broadcast(uid, src=src, group=self.group)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        call("b2_slab_comm_init", self.handle, C.c_char_p(raw))
+        self.native = True
 
     def _push(self):
         from ._lib import call, ptr
@@ -387,12 +411,52 @@ class SlabSimul:
             call("b2_slab_zfwd", h, f, f + 1, sp)
         call("b2_slab_rk", h, scheme_id, stage, self.deltat, ptr(Sin), ptr(self.state_spect), ptr(tout), sp)
 
+    def _set_stage_layout(self, prune):
+        from ._lib import call
+
+        pr = self._prune if (prune and self._prune is not None) else None
+        if pr is None and self.lean:
+            raise ValueError("lean slab buffers hold the pruned exchange only: the input must be dealiased "
+                             "(SlabSimul(..., lean=False) handles arbitrary states)")
+        if pr is None:
+            call("b2_slab_set_pruning", self.handle, 0, 0, 0, 0, 0, 0, 0, 0)
+        else:
+            call("b2_slab_set_pruning", self.handle, 1, *pr["args"])
+        call("b2_slab_set_chunks", self.handle, self.nchunks)
+
+    def _native_step(self, sid, prune):
+        """One C call per time step: FFT passes, NCCL all-to-alls and epilogues inside the library."""
+        from ._lib import call, ptr, stream_ptr
+
+        self._set_stage_layout(prune)
+        tr = self.torch
+        if self.use_cfl:
+            # CFL on the device with the GLOBAL max |v| (base/time_stepping/base.py:320-354)
+            if self._dt_dev is None:
+                self._dt_dev = tr.full((1,), float(self.deltat), dtype=tr.float64, device=self.device)
+                self._vmax_dev = tr.zeros(3, dtype=tr.float64, device=self.device)
+            else:
+                self._dt_dev.fill_(float(self.deltat))
+            ts = self.params.time_stepping
+            cfl = ts.cfl_coef if getattr(ts, "cfl_coef", None) else (1.0 if self.scheme == "RK4" else 0.4)
+            call("b2_slab_time_step_cfl", self.handle, sid, float(cfl), float(ts.deltat_max), ptr(self._dt_dev),
+                 ptr(self._vmax_dev), ptr(self.state_spect), stream_ptr())
+            self.deltat = float(self._dt_dev.item())
+        else:
+            call("b2_slab_time_step", self.handle, sid, float(self.deltat), ptr(self.state_spect), stream_ptr())
+
     def tendencies_nonlin(self, state_spect=None, old=None):
         if self.lean:
             raise ValueError("tendencies_nonlin on arbitrary input needs the full-size buffers (lean=False)")
         src = self.state_spect if state_spect is None else state_spect
         out = self.torch.empty_like(self.state_spect) if old is None else old
-        self._run_stage(src, True, SCHEME_IDS[self.scheme], -1, out)
+        if self.native:
+            from ._lib import call, ptr, stream_ptr
+
+            self._set_stage_layout(False)
+            call("b2_slab_tendencies", self.handle, ptr(src), ptr(out), stream_ptr())
+        else:
+            self._run_stage(src, True, SCHEME_IDS[self.scheme], -1, out)
         return out
 
     def one_time_step(self):
@@ -401,9 +465,14 @@ class SlabSimul:
         if self.use_pruning and not self._state_dealiased and self.where_dealiased is not None:
             self._state_dealiased = self._check_dealiased()
         prune = self.use_pruning and self._state_dealiased
-        for st in range(nstages):
-            Sin = self.state_spect if st == 0 else self._stagebuf
-            self._run_stage(Sin, st == 0, sid, st, prune=prune)
+        if self.native:
+            self._native_step(sid, prune)
+        else:
+            if bool(getattr(self.params.time_stepping, "USE_CFL", False)) and self.use_cfl:
+                raise NotImplementedError("CFL on slab plans needs the native collectives (NCCL)")
+            for st in range(nstages):
+                Sin = self.state_spect if st == 0 else self._stagebuf
+                self._run_stage(Sin, st == 0, sid, st, prune=prune)
         self._state_dealiased = True  # the last stage projects and dealiases the state
         self.t += self.deltat
         self.it += 1

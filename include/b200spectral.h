@@ -208,6 +208,26 @@ int b2_slab_phase_b(b2_plan* p, void* stream);
 int b2_slab_phase_c(b2_plan* p, int scheme, int stage, double dt, const double* S_in, double* S,
                     double* T_out, void* stream);
 
+/* ---- native collectives: the communicator belongs to the plan, so a host
+ * in any language drives the multi-GPU path with one call per time step.  NCCL (libnccl.so.2) is
+ * bound at run time.  Rank 0 calls b2_nccl_unique_id, the host broadcasts the 128 bytes (MPI_Bcast,
+ * torch.distributed, a file ...), every rank calls b2_slab_comm_init.  The all-to-alls are grouped
+ * ncclSend / ncclRecv on a stream owned by the plan, overlapped with the FFT passes exactly like the
+ * host-orchestrated schedule above; they replace the MPI transposes inside fluidfft's
+ * fft3d.mpi_with_fftwmpi3d.fft_as_arg / ifft_as_arg. */
+int b2_nccl_unique_id(void* out128);
+int b2_slab_comm_init(b2_plan* p, const void* uid128);
+int b2_slab_comm_destroy(b2_plan* p);
+/* T_out = N(S_in) on a slab plan (Simul.tendencies_nonlin under MPI) */
+int b2_slab_tendencies(b2_plan* p, const double* S_in, double* T_out, void* stream);
+/* one full RK2 / RK4 step on a slab plan (TimeSteppingPseudoSpectral._time_step_RK2/4 +
+ * one_time_step_computation's project / dealias under MPI) */
+int b2_slab_time_step(b2_plan* p, int scheme, double dt, double* S, void* stream);
+/* the same with the CFL time increment from the GLOBAL max |v_i| (ncclAllReduce MAX replaces the
+ * mpi.comm.allreduce of base/time_stepping/base.py:25-26,320-354) */
+int b2_slab_time_step_cfl(b2_plan* p, int scheme, double cfl, double deltat_max, double* dt_dev,
+                          double* vmax_dev, double* S, void* stream);
+
 /* one step with the CFL time increment (base/time_stepping/base.py:320-354) decided on the device:
  * the max |v_i| are a side output of the stage-0 fused x pass (no extra pass over memory, no
  * state_phys), dt_dev (device double, in/out) carries deltat with the 2 % hysteresis, vmax_dev = 3
