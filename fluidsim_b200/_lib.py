@@ -64,6 +64,7 @@ SIGNATURES = {
     "b2_sum": [_p, _ll, _p, _p],
     "b2_set_physics": [_p, _i, _d, _d, _d, _d, _i, _d, _d, _d, _p],
     "b2_set_pruning": [_p, _i],
+    "b2_set_no_vz_kz0": [_p, _i],
     "b2_get_pruning_bounds": [_p, C.POINTER(_i)],
     "b2_check_dealiased": [_p, _p, _i, _p, _p, _p],
     "b2_work_fields": [_p, _i, C.POINTER(_i), C.POINTER(_i)],
@@ -108,7 +109,8 @@ for _name, _args in SIGNATURES.items():
     _fn.argtypes = _args
     _fn.restype = _RESTYPES.get(_name, _i)
 
-SOLVER_IDS = {"ns3d": 0, "ns3d.strat": 1, "ns2d": 2}
+# ns3d.bouss is the stratified kernel without the -N^2 vz coupling (bouss/solver.py:166): N = 0
+SOLVER_IDS = {"ns3d": 0, "ns3d.strat": 1, "ns3d.bouss": 1, "ns2d": 2}
 SCHEME_IDS = {"RK2": 2, "RK4": 4}
 
 

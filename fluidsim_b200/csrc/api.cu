@@ -1121,6 +1121,14 @@ extern "C" int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, do
     return compute_mask_bounds(p);
 }
 
+/* params.no_vz_kz0 (solvers/ns3d/solver.py:135-137, 260-263): vz(kz = 0) = 0 (and b) after every
+ * projection of the tendencies and of the state */
+extern "C" int b2_set_no_vz_kz0(b2_plan* p, int on) {
+    if (on && p->ndim != 3) return b2i_set_error("b2_set_no_vz_kz0: 3-D solvers only");
+    p->no_vz_kz0 = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar) {
     switch (solver) {
         case B2_SOLVER_NS3D: *nwork = 6; *nvar = 3; return 0;
@@ -1151,6 +1159,7 @@ struct RKArgs {
     const uint8_t* mask;
     long long fsize;
     double dt, N2;
+    int no_vz_kz0;    // solvers/ns3d/solver.py:260-263
     const double* dt_ptr;  // device-resident time increment (CFL steps); overrides dt when set
 };
 
@@ -1184,6 +1193,11 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
             T[3] = make_double2(di - a.N2 * vz.x, -dr - a.N2 * vz.y);
         }
         if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, T[0], T[1], T[2]);
+        const bool kz0 = SOLVER != B2_SOLVER_NS2D && a.no_vz_kz0 && Kz == 0.0;
+        if (kz0) {  // dealiasing_variable(vz_fft, where_kz_0) (+ b_fft), solver.py:260-263
+            T[2] = make_double2(0.0, 0.0);
+            if (SOLVER == B2_SOLVER_NS3D_STRAT) T[NV - 1] = make_double2(0.0, 0.0);
+        }
         if (masked) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) T[v] = make_double2(0.0, 0.0);
@@ -1254,6 +1268,10 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
         if (MODE == M_RK4_3 || MODE == M_RK2_1) {
             // end of step: project_state_spect + dealiasing (solvers/ns3d/time_stepping.py:15-16)
             if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, Sn[0], Sn[1], Sn[2]);
+            if (kz0) {
+                Sn[2] = make_double2(0.0, 0.0);
+                if (SOLVER == B2_SOLVER_NS3D_STRAT) Sn[NV - 1] = make_double2(0.0, 0.0);
+            }
 #pragma unroll
             for (int v = 0; v < NV; ++v)
                 a.S[v * a.fsize + i] = masked ? make_double2(0.0, 0.0) : Sn[v];
@@ -1460,6 +1478,7 @@ static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     a.dt = dt;
     a.dt_ptr = nullptr;
     a.N2 = p->N * p->N;
+    a.no_vz_kz0 = p->no_vz_kz0;
     a.fcor = p->has_f ? p->f : 0.0;
     return a;
 }

@@ -43,7 +43,7 @@ def create_default_params(solver="ns3d"):
     p.nu_4 = 0.0
     p.nu_8 = 0.0
     p.nu_m4 = 0.0
-    if solver in ("ns3d", "ns3d.strat"):
+    if solver in ("ns3d", "ns3d.strat", "ns3d.bouss"):
         p._set_child(
             "oper",
             dict(

@@ -60,7 +60,7 @@ class SimulBasePseudoSpectralB200:
         return (
             float(p.nu_2), float(p.nu_4), float(p.nu_8), float(p.nu_m4),
             0 if f is None else 1, 0.0 if f is None else float(f),
-            float(getattr(p, "N", 0.0)), float(getattr(p, "beta", 0.0)),
+            0.0 if self.short_name == "ns3d.bouss" else float(getattr(p, "N", 0.0)), float(getattr(p, "beta", 0.0)),
         )
 
     def _mask_for_fused(self):
@@ -93,6 +93,8 @@ class SimulBasePseudoSpectralB200:
         call("b2_set_physics", h, SOLVER_IDS[self.short_name], *self._physics_args(), ptr(mask))
         call("b2_set_buffers", h, ptr(acc), ptr(stage), ptr(work))
         call("b2_set_aliasing", h, 1 if alias else 0)
+        if self.ndim == 3:
+            call("b2_set_no_vz_kz0", h, 1 if getattr(self, "no_vz_kz0", False) else 0)
 
     def mask_modified(self):
         """Call after editing ``oper.where_dealiased`` in place: the kept ranges of the pruned
@@ -144,8 +146,9 @@ class SimulNS3D(SimulBasePseudoSpectralB200):
 
     def _init_projection(self):
         """solver.py:147-174: only the default projection is on the GPU path."""
-        if getattr(self.params, "no_vz_kz0", False):
-            raise NotImplementedError("no_vz_kz0 is not implemented on the GPU path")
+        self.no_vz_kz0 = bool(getattr(self.params, "no_vz_kz0", False))
+        if self.no_vz_kz0:  # solver.py:153-157
+            self.where_kz_0 = self.oper.Kz.abs() == 0.0
         projection = getattr(self.params, "projection", None)
         if projection is None:
             self._projector = self.oper.project_perpk3d
@@ -219,6 +222,10 @@ class SimulNS3D(SimulBasePseudoSpectralB200):
         self._projector(
             state_spect.get_var("vx_fft"), state_spect.get_var("vy_fft"), state_spect.get_var("vz_fft")
         )
+        if self.no_vz_kz0:
+            state_spect.get_var("vz_fft")[self.where_kz_0] = 0.0
+            if "b_fft" in state_spect.keys:
+                state_spect.get_var("b_fft")[self.where_kz_0] = 0.0
 
 
 class SimulNS3DStrat(SimulNS3D):
@@ -226,6 +233,7 @@ class SimulNS3DStrat(SimulNS3D):
 
     short_name = "ns3d.strat"
     State = StateNS3DStrat
+    _N_coupling = None  # None: params.N (ns3d.bouss overrides with 0)
 
     def _extra_tendencies(self, tendencies_fft, spect_get_var, state_spect, vx, vy, vz):
         """strat/solver.py:198-211: fz += b ; fb = -div(v b) - N^2 vz."""
@@ -240,8 +248,17 @@ class SimulNS3DStrat(SimulNS3D):
             b = self.fields_tmp[3]
             oper.ifft_as_arg(b_fft, b)
         div_vb_fft = oper.div_vb_fft_from_vb(vx, vy, vz, b)
-        call("b2_compute_fb_fft", ptr(div_vb_fft), float(self.params.N), ptr(vz_fft), div_vb_fft.numel(), stream_ptr())
+        N = self._N_coupling if self._N_coupling is not None else float(self.params.N)
+        call("b2_compute_fb_fft", ptr(div_vb_fft), float(N), ptr(vz_fft), div_vb_fft.numel(), stream_ptr())
         tendencies_fft.set_var("b_fft", div_vb_fft)
+
+
+class SimulNS3DBouss(SimulNS3DStrat):
+    """solvers/ns3d/bouss/solver.py:99-175: the stratified solver without the background
+    stratification term, fb = -div(v b) (fz += b kept).  Same kernels with N = 0."""
+
+    short_name = "ns3d.bouss"
+    _N_coupling = 0.0
 
 
 class SimulNS2D(SimulBasePseudoSpectralB200):
@@ -294,7 +311,7 @@ class SimulNS2D(SimulBasePseudoSpectralB200):
         return tendencies_fft
 
 
-SIMUL_CLASSES = {"ns3d": SimulNS3D, "ns3d.strat": SimulNS3DStrat, "ns2d": SimulNS2D}
+SIMUL_CLASSES = {"ns3d": SimulNS3D, "ns3d.strat": SimulNS3DStrat, "ns3d.bouss": SimulNS3DBouss, "ns2d": SimulNS2D}
 
 
 def make_simul(solver, params, fused=None):

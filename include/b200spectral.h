@@ -134,6 +134,9 @@ int b2_sum(const double* x, long long n, double* out_dev, void* stream);
  * mask = where_dealiased (uint8, K-shaped, device; may be NULL = no dealiasing) */
 int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4, int has_f,
                    double f, double N, double beta, const uint8_t* mask);
+/* params.no_vz_kz0 (solvers/ns3d/solver.py:135-137, 260-263): vz (and b) are zeroed at kz = 0
+ * after every projection of the tendencies and of the end-of-step state */
+int b2_set_no_vz_kz0(b2_plan* p, int on);
 /* dealias-pruned transforms: with on != 0 the fused path visits only the bounding box of the modes
  * kept by the mask (exact: everything outside is zero).  Requires the state to be dealiased, which
  * holds after every step (solvers/ns3d/time_stepping.py:16); off by default. */

@@ -244,9 +244,9 @@ def make_params(solver, nx, ny, nz=None, Lx=2 * np.pi, Ly=2 * np.pi, Lz=2 * np.p
     p._set_child("forcing", dict(enable=False))
     if solver.startswith("ns3d"):
         p.f = kw.pop("f", None)
-        p.no_vz_kz0 = False
+        p.no_vz_kz0 = bool(kw.pop("no_vz_kz0", False))
         p.projection = None
-    if solver == "ns3d.strat":
+    if solver in ("ns3d.strat", "ns3d.bouss"):
         p.N = kw.pop("N", 1.0)
     if solver == "ns2d":
         p.beta = kw.pop("beta", 0.0)
@@ -281,6 +281,12 @@ class RefSim:
         statemod, statecls, tsmod, tscls = {
             "ns3d": ("ns3d.state", "StateNS3D", "ns3d.time_stepping", "TimeSteppingPseudoSpectralNS3D"),
             "ns3d.strat": (
+                "ns3d.strat.state",
+                "StateNS3DStrat",
+                "ns3d.time_stepping",
+                "TimeSteppingPseudoSpectralNS3D",
+            ),
+            "ns3d.bouss": (
                 "ns3d.strat.state",
                 "StateNS3DStrat",
                 "ns3d.time_stepping",

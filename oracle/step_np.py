@@ -94,10 +94,12 @@ class OracleSim:
         N=1.0,
         f=None,
         beta=0.0,
+        no_vz_kz0=False,
     ):
         self.solver = solver
         self.nu_2, self.nu_4, self.nu_8, self.nu_m4 = nu_2, nu_4, nu_8, nu_m4
         self.N, self.f, self.beta = N, f, beta
+        self.no_vz_kz0 = bool(no_vz_kz0)
         self.deltat = float(deltat0)
         self.scheme = type_time_scheme
         self.it = 0
@@ -111,12 +113,12 @@ class OracleSim:
             self.oper.Lx, self.oper.Ly = self.oper.lx, self.oper.ly
             keys_spect = ["rot_fft"]
             keys_phys = ["ux", "uy", "rot"]
-        elif solver in ("ns3d", "ns3d.strat"):
+        elif solver in ("ns3d", "ns3d.strat", "ns3d.bouss"):
             self.ndim = 3
             self.oper = OperatorsPseudoSpectral3D(
                 nx, ny, nz, Lx, Ly, Lz, coef_dealiasing=coef_dealiasing
             )
-            keys_phys = ["vx", "vy", "vz"] + (["b"] if solver == "ns3d.strat" else [])
+            keys_phys = ["vx", "vy", "vz"] + (["b"] if solver in ("ns3d.strat", "ns3d.bouss") else [])
             keys_spect = [k + "_fft" for k in keys_phys]
         else:
             raise ValueError(solver)
@@ -193,10 +195,15 @@ class OracleSim:
 
     # ------------------------------------------------------------------ nonlinear terms
     def project_state_spect(self, state_spect):
-        """solvers/ns3d/solver.py:255-263 (projection=None, no_vz_kz0=False)."""
+        """solvers/ns3d/solver.py:255-263 (projection=None)."""
         self.oper.project_perpk3d(
             state_spect.get_var("vx_fft"), state_spect.get_var("vy_fft"), state_spect.get_var("vz_fft")
         )
+        if self.no_vz_kz0:  # solver.py:260-263
+            where_kz_0 = np.abs(self.oper.Kz) == 0.0
+            state_spect.get_var("vz_fft")[where_kz_0] = 0.0
+            if "b_fft" in state_spect.keys:
+                state_spect.get_var("b_fft")[where_kz_0] = 0.0
 
     def dealiasing(self, thing):
         """operators3d.py:336-342; operators2d.py:200-220."""
@@ -216,7 +223,7 @@ class OracleSim:
     def _tendencies_ns3d(self, state_spect=None, old=None):
         """solvers/ns3d/solver.py:180-253; strat extras solvers/ns3d/strat/solver.py:138-216."""
         oper = self.oper
-        strat = self.solver == "ns3d.strat"
+        strat = self.solver in ("ns3d.strat", "ns3d.bouss")
         get = (self.state_spect if state_spect is None else state_spect).get_var
         vx_fft, vy_fft, vz_fft = get("vx_fft"), get("vy_fft"), get("vz_fft")
         omegax_fft, omegay_fft, omegaz_fft = self.fields_spect_tmp
@@ -254,8 +261,10 @@ class OracleSim:
                 b = self.fields_tmp[3]
                 oper.ifft_as_arg(b_fft, b)
             div_vb_fft = oper.div_vb_fft_from_vb(vx, vy, vz, b)
-            # compute_fb_fft, strat/solver.py:29-33
-            fb_fft = -div_vb_fft - self.N**2 * vz_fft
+            if self.solver == "ns3d.bouss":  # bouss/solver.py:166
+                fb_fft = -div_vb_fft
+            else:  # compute_fb_fft, strat/solver.py:29-33
+                fb_fft = -div_vb_fft - self.N**2 * vz_fft
             tendencies_fft.set_var("b_fft", fb_fft)
         if self.forcing_fft is not None:  # solvers/ns3d/solver.py:243-244
             tendencies_fft += self.forcing_fft
@@ -460,7 +469,7 @@ class OracleSim:
             vmax = np.sqrt(vv[0] ** 2 + vv[1] ** 2 + vv[2] ** 2).max()
             vv = [velo_max * vi / vmax for vi in vv]
             fields = [oper.fft(vi) for vi in vv]
-            if self.solver == "ns3d.strat":
+            if self.solver in ("ns3d.strat", "ns3d.bouss"):
                 lambda0 = min(oper.Lx, oper.Ly, oper.Lz) / 4.0 if length is None else length
                 k0 = 2 * pi / lambda0
                 field = np.random.random(oper.shapeX_loc)

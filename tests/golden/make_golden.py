@@ -36,6 +36,10 @@ CASES = {
     "ns2d_32x32_rk4": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
     "ns2d_64x32_rk2_beta": ("ns2d", (64, 32), 5, dict(nu_2=1e-3, deltat0=1e-2, beta=0.4, type_time_scheme="RK2", Lx=8.0, Ly=8.0)),
     "ns2d_24x15_rk4_odd": ("ns2d", (24, 15), 3, dict(nu_2=1e-3, deltat0=2e-2, Lx=8.0, Ly=8.0, truncation_shape="no_multiple_aliases")),
+    # f-4 breadth: ns3d.bouss (solvers/ns3d/bouss/solver.py) and params.no_vz_kz0 (solver.py:260-263)
+    "bouss_16x16x16_rk4": ("ns3d.bouss", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2)),
+    "ns3d_16x16x16_rk4_novzkz0": ("ns3d", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, no_vz_kz0=True)),
+    "strat_16x16x8_rk2_novzkz0": ("ns3d.strat", (16, 16, 8), 4, dict(nu_4=1e-3, deltat0=1e-2, N=1.5, type_time_scheme="RK2", no_vz_kz0=True)),
     # forced cases: a constant forcing_fft on the shell 2 <= |k|/dk <= 3.5 handed to the reference's
     # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
     "ns3d_16x16x16_rk4_forced": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),

@@ -35,6 +35,7 @@ def _worker(rank, world, port, name, nchunks, dist_kind, lean, native, q):
         for key in ("Lx", "Ly", "Lz"):
             if key in kw:
                 setattr(p.oper, key, kw.pop(key))
+        p.time_stepping.USE_CFL = False  # the goldens are fixed-deltat runs
         p.time_stepping.type_time_scheme = kw.pop("type_time_scheme", "RK4")
         p.time_stepping.deltat0 = kw.pop("deltat0")
         for key in list(kw):
@@ -86,6 +87,18 @@ def _worker(rank, world, port, name, nchunks, dist_kind, lean, native, q):
                    float(np.abs(obs["E_spectrum3d"] - spec["E"]).max() / spec["E"].max()),
                    float(np.abs(obs["vy_ky"] - spec["vy_ky"]).max() / spec["E_ky"].max()),
                    float(np.abs(obs["vz_kz"] - spec["vz_kz"]).max() / spec["E_kz"].max()))
+        if native and solver == "ns3d":
+            # CFL on the slab plan: deltat from the GLOBAL max |v| (x-pass side output + ncclAllReduce MAX
+            # + device-side rule) against the oracle's _compute_time_increment_CLF_uxuyuz restatement
+            o.deltat = sim.deltat
+            o.scheme = sim.scheme
+            sim.use_cfl = True
+            for _ in range(2):
+                dt_o = o.compute_time_increment_CFL(cfl=1.0 if sim.scheme == "RK4" else 0.4, deltat_max=0.2)
+                o.one_time_step()
+                sim.one_time_step()
+                e_en = max(e_en, abs(sim.deltat - dt_o) / dt_o * 1e4)  # 1e-12 relative on deltat
+                e_n = max(e_n, rel_err(sim.gather_state(), np.array(o.state_spect)))
         q.put((rank, e_t, e_1, e_n, e_en))
     finally:
         dist.destroy_process_group()
