@@ -65,6 +65,9 @@ SIGNATURES = {
     "b2_set_physics": [_p, _i, _d, _d, _d, _d, _i, _d, _d, _d, _p],
     "b2_set_pruning": [_p, _i],
     "b2_set_no_vz_kz0": [_p, _i],
+    "b2_set_projection": [_p, _i],
+    "b2_project_toroidal": [_p, _p, _p, _p, _p],
+    "b2_project_poloidal": [_p, _p, _p, _p, _p],
     "b2_get_pruning_bounds": [_p, C.POINTER(_i)],
     "b2_check_dealiased": [_p, _p, _i, _p, _p, _p],
     "b2_work_fields": [_p, _i, C.POINTER(_i), C.POINTER(_i)],

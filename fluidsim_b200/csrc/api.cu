@@ -335,6 +335,50 @@ B2_DEVINL void project3(double Kx, double Ky, double Kz, double invK2, cplx& a, 
     c.x -= Kz * tr; c.y -= Kz * ti;
 }
 
+// project_toroidal / project_poloidal (/root/reference/fluidsim/operators/operators3d.py:911-958,
+// 788-856), same operation order as the reference's array expressions
+B2_DEVINL void project_toroidal3(double Kx, double Ky, cplx& a, cplx& b, cplx& c) {
+    double Kh2 = Kx * Kx + Ky * Ky;
+    if (Kh2 == 0.0) Kh2 = 1e-14;
+    const double tmp = sqrt(1.0 / Kh2);
+    const double cphi = Kx * tmp, sphi = Ky * tmp;
+    const double tr = -sphi * a.x + cphi * b.x, ti = -sphi * a.y + cphi * b.y;
+    a = make_double2(-sphi * tr, -sphi * ti);
+    b = make_double2(cphi * tr, cphi * ti);
+    c = make_double2(0.0, 0.0);
+}
+B2_DEVINL void project_poloidal3(double Kx, double Ky, double Kz, cplx& a, cplx& b, cplx& c) {
+    const double Kh2 = Kx * Kx + Ky * Ky;
+    double K2nz = Kh2 + Kz * Kz, Kh2nz = Kh2;
+    if (Kh2nz == 0.0) Kh2nz = 1e-14;
+    if (K2nz == 0.0) K2nz = 1e-14;
+    const double invKh = 1.0 / Kh2nz, invK = 1.0 / K2nz;
+    const double cth = Kz * sqrt(invK), sth = sqrt(Kh2 * invK);
+    const double cphi = Kx * sqrt(invKh), sphi = Ky * sqrt(invKh);
+    const double cc = cth * cphi, cs = cth * sphi;
+    const double tr = cc * a.x + cs * b.x - sth * c.x, ti = cc * a.y + cs * b.y - sth * c.y;
+    a = make_double2(cc * tr, cc * ti);
+    b = make_double2(cs * tr, cs * ti);
+    c = make_double2(-sth * tr, -sth * ti);
+}
+// params.projection dispatch (solvers/ns3d/solver.py:158-174)
+B2_DEVINL void project_any(int projection, double Kx, double Ky, double Kz, double invK2, cplx& a, cplx& b, cplx& c) {
+    if (projection == 0) project3(Kx, Ky, Kz, invK2, a, b, c);
+    else if (projection == 1) project_toroidal3(Kx, Ky, a, b, c);
+    else project_poloidal3(Kx, Ky, Kz, a, b, c);
+}
+
+__global__ void project_tp_kernel(KGrid g, cplx* vx, cplx* vy, cplx* vz, int projection) {
+    B2_ROW_SETUP
+    for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
+        const double Kx = g.kx[ikx];
+        const long long i = rbase + ikx;
+        cplx a = vx[i], b = vy[i], c = vz[i];
+        project_any(projection, Kx, Ky, Kz, 0.0, a, b, c);
+        vx[i] = a; vy[i] = b; vz[i] = c;
+    }
+}
+
 __global__ void project_kernel(KGrid g, cplx* vx, cplx* vy, cplx* vz) {
     B2_ROW_SETUP
     for (int ikx = threadIdx.x; ikx < g.nkx; ikx += blockDim.x) {
@@ -451,6 +495,18 @@ extern "C" int b2_project_perpk3d(b2_plan* p, double* vx, double* vy, double* vz
     project_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (cplx*)vx, (cplx*)vy,
                                                                            (cplx*)vz);
     B2_LAUNCH_CHECK("project_kernel");
+    return 0;
+}
+extern "C" int b2_project_toroidal(b2_plan* p, double* vx, double* vy, double* vz, void* stream) {
+    project_tp_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (cplx*)vx, (cplx*)vy,
+                                                                              (cplx*)vz, 1);
+    B2_LAUNCH_CHECK("project_tp_kernel");
+    return 0;
+}
+extern "C" int b2_project_poloidal(b2_plan* p, double* vx, double* vy, double* vz, void* stream) {
+    project_tp_kernel<<<nrows(p), B2_ROW_THREADS, 0, (cudaStream_t)stream>>>(kgrid(p), (cplx*)vx, (cplx*)vy,
+                                                                              (cplx*)vz, 2);
+    B2_LAUNCH_CHECK("project_tp_kernel");
     return 0;
 }
 extern "C" int b2_vector_product(const double* ax, const double* ay, const double* az, double* bx,
@@ -1129,6 +1185,15 @@ extern "C" int b2_set_no_vz_kz0(b2_plan* p, int on) {
     return 0;
 }
 
+/* params.projection (solvers/ns3d/solver.py:139-174): 0 = None (project_perpk3d), 1 = "toroidal" /
+ * "vortical" (operators3d.py:911-958), 2 = "poloidal" (operators3d.py:788-856) */
+extern "C" int b2_set_projection(b2_plan* p, int projection) {
+    if (projection < 0 || projection > 2) return b2i_set_error("b2_set_projection: unknown projection %d", projection);
+    if (projection && p->ndim != 3) return b2i_set_error("b2_set_projection: 3-D solvers only");
+    p->projection = projection;
+    return 0;
+}
+
 extern "C" int b2_work_fields(const b2_plan* p, int solver, int* nwork, int* nvar) {
     switch (solver) {
         case B2_SOLVER_NS3D: *nwork = 6; *nvar = 3; return 0;
@@ -1159,6 +1224,7 @@ struct RKArgs {
     const uint8_t* mask;
     long long fsize;
     double dt, N2;
+    int projection;   // params.projection (0 perpk3d, 1 toroidal, 2 poloidal)
     int no_vz_kz0;    // solvers/ns3d/solver.py:260-263
     const double* dt_ptr;  // device-resident time increment (CFL steps); overrides dt when set
 };
@@ -1192,7 +1258,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
             // div = i (dr + i di) = (-di, dr);  fb = -div - N^2 vz
             T[3] = make_double2(di - a.N2 * vz.x, -dr - a.N2 * vz.y);
         }
-        if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, T[0], T[1], T[2]);
+        if (SOLVER != B2_SOLVER_NS2D) project_any(a.projection, Kx, Ky, Kz, invK2, T[0], T[1], T[2]);
         const bool kz0 = SOLVER != B2_SOLVER_NS2D && a.no_vz_kz0 && Kz == 0.0;
         if (kz0) {  // dealiasing_variable(vz_fft, where_kz_0) (+ b_fft), solver.py:260-263
             T[2] = make_double2(0.0, 0.0);
@@ -1267,7 +1333,7 @@ __global__ void __launch_bounds__(B2_ROW_THREADS) rk_stage_kernel(RKArgs a) {
         }
         if (MODE == M_RK4_3 || MODE == M_RK2_1) {
             // end of step: project_state_spect + dealiasing (solvers/ns3d/time_stepping.py:15-16)
-            if (SOLVER != B2_SOLVER_NS2D) project3(Kx, Ky, Kz, invK2, Sn[0], Sn[1], Sn[2]);
+            if (SOLVER != B2_SOLVER_NS2D) project_any(a.projection, Kx, Ky, Kz, invK2, Sn[0], Sn[1], Sn[2]);
             if (kz0) {
                 Sn[2] = make_double2(0.0, 0.0);
                 if (SOLVER == B2_SOLVER_NS3D_STRAT) Sn[NV - 1] = make_double2(0.0, 0.0);
@@ -1479,6 +1545,7 @@ static RKArgs rk_args(b2_plan* p, const cplx* Sin, cplx* S, double dt) {
     a.dt_ptr = nullptr;
     a.N2 = p->N * p->N;
     a.no_vz_kz0 = p->no_vz_kz0;
+    a.projection = p->projection;
     a.fcor = p->has_f ? p->f : 0.0;
     return a;
 }
@@ -1686,7 +1753,8 @@ extern "C" int b2_slab_set_chunks(b2_plan* p, int nc) {
     return 0;
 }
 
-// y-inverse of fields [f0, f1), z chunk `chunk` (-1: all): xb -> (pruned: xa expanded | unpruned: xb)
+// y-inverse of fields [f0, f1), z chunk `chunk` (-1: all): xb (exchanged, rank-grouped kept rows) ->
+// xa (natural (zc, ny, pitch) array of the chunk)
 extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, int chunk, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e, nin, nout;
@@ -1699,7 +1767,7 @@ extern "C" int b2_slab_yinv(b2_plan* p, int f0, int f1, int chunk, void* stream)
     cplx* out[8];
     for (int f = f0; f < f1; ++f) {
         in[f - f0] = p->xb + f * p->xb_stride();
-        out[f - f0] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+        out[f - f0] = p->xa + f * p->xa_stride();
     }
     ProfScope ps(PC_Y_INV, s);
     for (int c = (chunk < 0 ? 0 : chunk); c < (chunk < 0 ? p->slab_nc : chunk + 1); ++c)
@@ -1715,7 +1783,7 @@ extern "C" int b2_slab_xpass(b2_plan* p, int chunk, void* stream) {
     if (chunk >= p->slab_nc) return b2i_set_error("b2_slab_xpass: bad chunk");
     const long long fs = p->fsize();
     cplx* XW[8];
-    for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+    for (int f = 0; f < nin; ++f) XW[f] = p->xa + f * p->xa_stride();
     const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
     const int pitch = p->prune ? p->keepx : p->nk;
     const long long lines_c = (long long)p->gy * (p->nzl / p->slab_nc);
@@ -1724,7 +1792,7 @@ extern "C" int b2_slab_xpass(b2_plan* p, int chunk, void* stream) {
     return b2i_xpass_fused(p, XW, lines_c, scale, pitch, pitch, lines_c * chunk, s);
 }
 
-// y-forward of output fields [f0, f1), z chunk `chunk` (-1: all): (pruned: xa -> xb compact | xb)
+// y-forward of output fields [f0, f1), z chunk `chunk` (-1: all): xa (natural) -> xb (exchanged)
 extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, int chunk, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     int e, nin, nout;
@@ -1736,7 +1804,7 @@ extern "C" int b2_slab_yfwd(b2_plan* p, int f0, int f1, int chunk, void* stream)
     const cplx* in[8];
     cplx* out[8];
     for (int f = f0; f < f1; ++f) {
-        in[f - f0] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+        in[f - f0] = p->xa + f * p->xa_stride();
         out[f - f0] = p->xb + f * p->xb_stride();
     }
     ProfScope ps(PC_Y_FWD, s);
@@ -1991,7 +2059,7 @@ static int slab_stage_native(b2_plan* p, int scheme, int stage, double dt, const
         {
             const long long fs_unused = 0; (void)fs_unused;
             cplx* XW[8];
-            for (int f = 0; f < nin; ++f) XW[f] = p->prune ? p->xa + f * p->xa_stride() : p->xb + f * p->xb_stride();
+            for (int f = 0; f < nin; ++f) XW[f] = p->xa + f * p->xa_stride();
             const double scale = 1.0 / ((double)p->gy * p->n1 * p->n2);
             const int pitch = p->prune ? p->keepx : p->nk;
             const long long lines_c = (long long)p->gy * (p->nzl / nc);

@@ -18,6 +18,7 @@ struct b2_plan {
     int solver;
     double nu2, nu4, nu8, num4, f, N, beta;
     int has_f;
+    int projection; // params.projection: 0 None (project_perpk3d), 1 toroidal / vortical, 2 poloidal
     int no_vz_kz0;  // params.no_vz_kz0: vz (and b) are zeroed at kz = 0 after every projection
     const uint8_t* mask;
     // caller-owned buffers (b2_set_buffers)

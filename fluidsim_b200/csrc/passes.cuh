@@ -16,23 +16,25 @@
 
 #define B2_MAXR 8  // ranks of a slab decomposition (one node)
 
-// Row map of the slab y passes: logical ky row i -> memory row of the exchanged array, whose rows
-// are grouped by owning rank (block or cyclic ky distribution) and hold only the kept rows of each
-// rank (the local dealiased band [lo, lo + gap) is not stored).
+// Row map of the slab y passes.  The exchanged (z-slab side) array of one z chunk is grouped by owning
+// rank: [rank r][z in chunk][kept local ky row of r][kx] -- rank r's block holds only its kept rows
+// (its local dealiased band [lo, lo + gap) is not stored) and starts blk[r] elements into the chunk.
+// Logical ky row i belongs to rank r = i / nyl (block) or i % P (cyclic ky distribution).
 struct RowMap {
     int P;  // 0: identity
     int nyl, cyclic;
     int shift;  // log2 of the divisor (P if cyclic, nyl otherwise) when it is a power of two, else -1
-    int rowstart[B2_MAXR], lo[B2_MAXR], gap[B2_MAXR];
-    B2_DEVINL int operator()(int i) const {
-        if (P == 0) return i;
-        if (P == 1) return i < lo[0] ? i : i - gap[0];  // block distribution: one global band
+    int lo[B2_MAXR], gap[B2_MAXR], nkr[B2_MAXR];
+    long long blk[B2_MAXR];
+    // element offset (without the kx column) of logical row i, plane z of the chunk
+    B2_DEVINL long long xoff(int i, int z, int pitch) const {
         const int d = cyclic ? P : nyl;
         const int q = shift >= 0 ? (i >> shift) : i / d;
         const int m = i - q * d;
         const int r = cyclic ? m : q;
         const int yl = cyclic ? q : m;
-        return rowstart[r] + (yl < lo[r] ? yl : yl - gap[r]);
+        const int ylc = yl < lo[r] ? yl : yl - gap[r];
+        return blk[r] + ((long long)z * nkr[r] + ylc) * pitch;
     }
 };
 
@@ -56,6 +58,7 @@ struct Geom {
     // (band rows are never touched)
     RowMap rows;
     int map_load, map_store;
+    int xpitch;     // kx pitch of the exchanged array (row map)
     int outer0;     // first outer index of this launch (chunked launches)
     // shape of the (n0, n1, nk) complex array the pass works on (TMA tensor maps, strided_tma.cuh);
     // dim_nk == 0: unknown -> LDG kernels only
@@ -71,7 +74,8 @@ static inline Geom geom_init() {
     g.outer_lo = 1 << 30; g.outer_gap = 0; g.band_lo = 0; g.band_hi = 0; g.skip_load = 0; g.skip_store = 0;
     g.wide = 0;
     g.rows.P = 0; g.rows.nyl = 1; g.rows.cyclic = 0; g.rows.shift = -1; g.map_load = 0; g.map_store = 0;
-    for (int r = 0; r < B2_MAXR; ++r) { g.rows.rowstart[r] = 0; g.rows.lo[r] = 0; g.rows.gap[r] = 0; }
+    g.xpitch = 0;
+    for (int r = 0; r < B2_MAXR; ++r) { g.rows.blk[r] = 0; g.rows.lo[r] = 0; g.rows.gap[r] = 0; g.rows.nkr[r] = 0; }
     g.outer0 = 0;
     g.dim_nk = 0; g.dim_n1 = 0; g.dim_n0 = 0;
     g.l2pf = 0;
@@ -127,9 +131,11 @@ __global__ void __launch_bounds__(TK*(N / E), (TK * (N / E) <= 256 ? 2 : 1))
     for (int m = 0; m < E; ++m) {
         const int i = t + m * T;
         const bool zero = !active || (g.skip_load && i >= g.band_lo && i < g.band_hi);
-        int il = i;
-        if constexpr (ROWMAP) il = (g.map_load && !zero) ? g.rows(i) : i;
-        x[m] = zero ? make_double2(0.0, 0.0) : ld(field, base + (long long)il * g.es, i, col, outer);
+        long long addr = base + (long long)i * g.es;
+        if constexpr (ROWMAP) {
+            if (g.map_load && !zero) addr = g.rows.xoff(i, outer, g.xpitch) + col;
+        }
+        x[m] = zero ? make_double2(0.0, 0.0) : ld(field, addr, i, col, outer);
     }
     if (g.l2pf > 0) {
         // tile of the CTA g.l2pf launches ahead (x fastest, then y)
@@ -147,9 +153,11 @@ __global__ void __launch_bounds__(TK*(N / E), (TK * (N / E) <= 256 ? 2 : 1))
                 for (int m = 0; m < E; ++m) {
                     const int i = t + m * T;
                     if (!(g.skip_load && i >= g.band_lo && i < g.band_hi)) {
-                        int il = i;
-                        if constexpr (ROWMAP) il = g.map_load ? g.rows(i) : i;
-                        ld.prefetch(pfield, pbase + (long long)il * g.es, i, pcol, pouter);
+                        long long paddr = pbase + (long long)i * g.es;
+                        if constexpr (ROWMAP) {
+                            if (g.map_load) paddr = g.rows.xoff(i, pouter, g.xpitch) + pcol;
+                        }
+                        ld.prefetch(pfield, paddr, i, pcol, pouter);
                     }
                 }
             }
@@ -161,9 +169,11 @@ __global__ void __launch_bounds__(TK*(N / E), (TK * (N / E) <= 256 ? 2 : 1))
         for (int m = 0; m < E; ++m) {
             const int i = t + m * T;
             if (!(g.skip_store && i >= g.band_lo && i < g.band_hi)) {
-                int is = i;
-                if constexpr (ROWMAP) is = g.map_store ? g.rows(i) : i;
-                st(field, base + (long long)is * g.es, i, col, outer, x[m]);
+                long long addr = base + (long long)i * g.es;
+                if constexpr (ROWMAP) {
+                    if (g.map_store) addr = g.rows.xoff(i, outer, g.xpitch) + col;
+                }
+                st(field, addr, i, col, outer, x[m]);
             }
         }
     }
@@ -493,9 +503,9 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
         const int i = idx / TK, c = idx % TK, col = col0 + c;
         cplx v = make_double2(0.0, 0.0);
         const bool inband_l = g.skip_load && i >= g.band_lo && i < g.band_hi;
-        const int il = (g.map_load && !inband_l) ? g.rows(i) : i;
-        if (col < g.ncols && !inband_l)
-            v = ld(field, (long long)outer * g.os + (long long)il * g.es + (long long)col * g.cs, i, col, outer);
+        long long addr_l = (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs;
+        if (g.map_load && !inband_l) addr_l = g.rows.xoff(i, outer, g.xpitch) + col;
+        if (col < g.ncols && !inband_l) v = ld(field, addr_l, i, col, outer);
         a[idx] = v;
     }
     __syncthreads();
@@ -530,9 +540,8 @@ __global__ void fft_generic_kernel(int N, int TK, Geom g, LoadOp ld, StoreOp st,
     for (int idx = threadIdx.x; idx < N * TK; idx += blockDim.x) {
         const int i = idx / TK, c = idx % TK, col = col0 + c;
         const bool inband_s = g.skip_store && i >= g.band_lo && i < g.band_hi;
-        const int is = (g.map_store && !inband_s) ? g.rows(i) : i;
-        if (col < g.ncols && !inband_s)
-            st(field, (long long)outer * g.os + (long long)is * g.es + (long long)col * g.cs, i, col, outer,
-               a[idx]);
+        long long addr_s = (long long)outer * g.os + (long long)i * g.es + (long long)col * g.cs;
+        if (g.map_store && !inband_s) addr_s = g.rows.xoff(i, outer, g.xpitch) + col;
+        if (col < g.ncols && !inband_s) st(field, addr_s, i, col, outer, a[idx]);
     }
 }

@@ -380,11 +380,12 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 
 // ------------------------------------------------------------------------------- slab passes
 // Index map between K-layout coordinates (yl = outer, z = i, kx = col) and the exchange layout of one
-// field: [z chunk c][peer q = z / nzl][kept local ky row][z within chunk][kx < pitch].  The z range of
-// every peer is cut in `nc` chunks so that the host can pipeline the all-to-all of chunk c+1 with
-// the y / x passes of chunk c; chunk regions are `cstride` elements apart (sized for the expanded
-// (ny, zc, pitch) array the y-inverse pass writes over the same region).  With pruning only the kept
-// local ky rows (compact index) and the kept kx columns are exchanged.
+// field: [z chunk c][peer q = z / nzl][z within chunk][kept local ky row][kx < pitch].  The z range of
+// every peer is cut in `nc` chunks so that the all-to-all of chunk c+1 overlaps the y / x passes of
+// chunk c; chunk regions are `cstride` elements apart.  Inside a peer block z is OUTSIDE ky: on the
+// receiving side the y passes then walk rows that are `pitch` elements apart (the access pattern of the
+// single-GPU y pass) instead of whole planes apart.  With pruning only the kept local ky rows (compact
+// index) and the kept kx columns are exchanged.
 struct SlabMapper {
     int nzl, nkl, pitch, y_lo, y_gap, zc;
     long long cstride;
@@ -394,7 +395,7 @@ struct SlabMapper {
         const int c = zl / zc;
         const int zlc = zl - c * zc;
         const int ylc = yl < y_lo ? yl : yl - y_gap;
-        return c * cstride + (((long long)q * nkl + ylc) * zc + zlc) * pitch + kx;
+        return c * cstride + (((long long)q * zc + zlc) * nkl + ylc) * pitch + kx;
     }
 };
 struct SlabStore {
@@ -454,63 +455,52 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
     return launch_strided<-1>(p->fast1, p->n1, g, nf, ld, st, p->tw1, s);
 }
 
-// y pass on the z-slab side, z chunk `chunk` (sub-array of zc = nz_loc / nc planes).  Unpruned: in
-// place on (ny, zc, nk).  Pruned: the exchanged array holds only the kept ky rows (compact) and
-// kx < keepx columns; the inverse pass expands it to all ny rows (in -> out), the forward pass
-// stores the kept rows back in compact form.  `in` / `out` are the field bases; the chunk offsets
-// (compact: nyk rows, expanded: ny rows) are applied here.
+// y pass on the z-slab side, z chunk `chunk` (sub-array of zc = nz_loc / nc planes).  One side of the
+// pass is the exchanged array (rows grouped by owning rank, only kept ky rows and kx < pitch columns:
+// RowMap), the other the natural array (zc, ny, pitch) the fused x pass works on: the inverse pass
+// expands exchanged -> natural (in -> out), the forward pass stores the kept rows back.  `in` / `out`
+// are the field bases; the chunk offsets (exchanged: kept rows, natural: ny rows) are applied here.
 int b2i_slab_ypass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out, int nf, int chunk,
                    cudaStream_t s) {
     if (nf > B2_MAXF) return b2i_set_error("too many fields");
     Geom g = geom_init();
     const int pitch = p->prune ? p->keepx : p->nk;
     const int zc = p->nzl / p->slab_nc;
-    const int nyk = p->prune ? p->gy - (p->gyk_hi - p->gyk_lo) : p->gy;
-    const long long cs_full = (long long)p->gy * zc * pitch, cs_compact = (long long)nyk * zc * pitch;
-    g.ncols = zc * pitch;
-    g.es = (long long)zc * pitch;
+    g.ncols = pitch;
+    g.nouter = zc;
+    g.es = pitch;
+    g.os = (long long)p->gy * pitch;
     g.nf = nf;
-    g.wide = 1;
-    long long in_off = chunk * cs_full, out_off = chunk * cs_full;
-    if (p->prune || p->ky_cyclic) {
-        // the exchanged array has its rows grouped by owning rank (kept rows only when pruned): the
-        // inverse pass reads it through the row map and writes natural ky order, the forward pass
-        // does the opposite
-        if (!p->ky_cyclic) {
-            // block distribution: ranks own increasing ky ranges, so the rank-grouped compact rows
-            // are simply the global rows with the dealiased band removed
-            g.rows.P = 1;
-            g.rows.nyl = p->gy;
-            g.rows.rowstart[0] = 0;
-            g.rows.lo[0] = p->gyk_lo;
-            g.rows.gap[0] = p->gyk_hi - p->gyk_lo;
-        } else {
-            g.rows.P = p->nranks;
-            g.rows.nyl = p->nyl;
-            g.rows.cyclic = 1;
-            g.rows.shift = -1;
-            if ((p->nranks & (p->nranks - 1)) == 0) {
-                int sh = 0;
-                while ((1 << sh) < p->nranks) ++sh;
-                g.rows.shift = sh;
-            }
-            int start = 0;
-            for (int r = 0; r < p->nranks; ++r) {
-                int lo, hi;
-                b2i_slab_local_band(p, r, &lo, &hi);
-                g.rows.rowstart[r] = start;
-                g.rows.lo[r] = lo;
-                g.rows.gap[r] = hi - lo;
-                start += p->nyl - (hi - lo);
-            }
-        }
-        if (dir > 0) g.map_load = 1; else g.map_store = 1;
+    g.xpitch = pitch;
+    g.rows.P = p->nranks;
+    g.rows.nyl = p->nyl;
+    g.rows.cyclic = p->ky_cyclic ? 1 : 0;
+    g.rows.shift = -1;
+    const int divisor = p->ky_cyclic ? p->nranks : p->nyl;
+    if ((divisor & (divisor - 1)) == 0) {
+        int sh = 0;
+        while ((1 << sh) < divisor) ++sh;
+        g.rows.shift = sh;
     }
+    long long start = 0;
+    for (int r = 0; r < p->nranks; ++r) {
+        int lo, hi;
+        b2i_slab_local_band(p, r, &lo, &hi);
+        g.rows.lo[r] = lo;
+        g.rows.gap[r] = hi - lo;
+        g.rows.nkr[r] = p->nyl - (hi - lo);
+        g.rows.blk[r] = start;
+        start += (long long)g.rows.nkr[r] * zc * pitch;
+    }
+    const long long cs_x = start;                       // exchanged chunk
+    const long long cs_n = (long long)p->gy * zc * pitch;  // natural chunk
+    long long in_off, out_off;
+    if (dir > 0) { g.map_load = 1; in_off = chunk * cs_x; out_off = chunk * cs_n; }
+    else { g.map_store = 1; in_off = chunk * cs_n; out_off = chunk * cs_x; }
     if (p->prune) {
         g.band_lo = p->gyk_lo;
         g.band_hi = p->gyk_hi;
-        if (dir > 0) { g.skip_load = 1; in_off = chunk * cs_compact; }
-        else { g.skip_store = 1; out_off = chunk * cs_compact; }
+        if (dir > 0) g.skip_load = 1; else g.skip_store = 1;
     }
     PlainIn ld;
     PlainStore st;

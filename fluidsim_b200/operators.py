@@ -189,6 +189,14 @@ class OperatorsPseudoSpectral3D(_OperatorBase):
     def project_perpk3d(self, vx_fft, vy_fft, vz_fft):
         call("b2_project_perpk3d", self.plan.handle, ptr(vx_fft), ptr(vy_fft), ptr(vz_fft), stream_ptr())
 
+    def project_toroidal(self, vx_fft, vy_fft, vz_fft):
+        """operators3d.py:911-958 (in place)."""
+        call("b2_project_toroidal", self.plan.handle, ptr(vx_fft), ptr(vy_fft), ptr(vz_fft), stream_ptr())
+
+    def project_poloidal(self, vx_fft, vy_fft, vz_fft):
+        """operators3d.py:788-856 (in place)."""
+        call("b2_project_poloidal", self.plan.handle, ptr(vx_fft), ptr(vy_fft), ptr(vz_fft), stream_ptr())
+
     def rotfft_from_vecfft_outin(self, vx_fft, vy_fft, vz_fft, rotxfft, rotyfft, rotzfft):
         call(
             "b2_rotfft_from_vecfft", self.plan.handle, ptr(vx_fft), ptr(vy_fft), ptr(vz_fft),

@@ -8,11 +8,11 @@ Decomposition (the layout fluidsim already handles for
 * spectral side: split along ky -> local K layout ``(ny_loc, nz, nx/2+1)``, ``dimX_K = (1, 0, 2)``
 
 One RK stage = phase A (z-inverse written straight into the exchange layout: the "pack" is fused
-into the FFT store), all-to-all, phase B (y-inverse, fused x pass, y-forward, in place on the
-received blocks: no "unpack" pass either), all-to-all, phase C (z-forward reading the exchange
-layout + RK epilogue).  The exchange layout of a field is ``[peer][ky_loc][z_loc][kx]``, so each
-all-to-all moves ``world`` equal contiguous blocks per field and the received buffer *is* the
-``(ny, nz_loc, nk)`` array the y pass wants.
+into the FFT store), all-to-all, phase B (y-inverse straight from the received blocks into the natural ``(nz_loc, ny, nk)``
+array: the "unpack" is fused into the FFT load; fused x pass; y-forward back into the exchange
+layout), all-to-all, phase C (z-forward reading the exchange layout + RK epilogue).  The exchange
+layout of a field is ``[z chunk][peer][z in chunk][ky_loc][kx]``: each all-to-all moves ``world``
+contiguous blocks per field, and with z outside ky in a block the y passes walk rows ``nk`` apart.
 
 The functions ``local_from_global`` / ``global_from_local`` / ``exchange_index`` define the layout
 algebra and are exercised on CPU (gloo, world_size 2) in ``tests/test_slab_cpu.py``.
@@ -53,26 +53,28 @@ def global_from_local(parts, cyclic=False):
     return out
 
 
-def exchanged_row(i, world, nyl, cyclic=False):
-    """Row of the z-slab-side (received) array holding global ky row ``i`` (unpruned): rows are
-    grouped by owning rank (``RowMap`` in csrc/passes.cuh)."""
-    if cyclic:
-        return (i % world) * nyl + i // world
-    return i
-
-
 def exchange_index(z, kx, yl, nzl, nyl, nk, nchunks=1, ny=None):
     """Offset of K-layout element (yl, z, kx) in the exchange layout
-    [z chunk][peer][ky_loc][z in chunk][kx] (restated by ``SlabMapper`` in csrc/strided.cu; unpruned
+    [z chunk][peer][z in chunk][ky_loc][kx] (restated by ``SlabMapper`` in csrc/strided.cu; unpruned
     case: every local ky row and kx column is exchanged).  Chunk regions are ``ny * zc * nk``
-    elements apart."""
+    elements apart.  Inside a peer block z runs OUTSIDE ky, so that the receiving side's y passes
+    walk rows ``nk`` apart (the single-GPU y-pass access pattern)."""
     r = z // nzl
     zl = z - r * nzl
     zc = nzl // nchunks
     c = zl // zc
     zlc = zl - c * zc
     cstride = 0 if nchunks == 1 else ny * zc * nk
-    return c * cstride + ((r * nyl + yl) * zc + zlc) * nk + kx
+    return c * cstride + ((r * zc + zlc) * nyl + yl) * nk + kx
+
+
+def natural_from_exchanged(chunk, world, zc, nyl, nk, cyclic=False):
+    """Received chunk (flat) ``[rank r][z in chunk][ky_loc of r][kx]`` -> natural ``(zc, ny, nk)`` (what
+    the y-inverse pass does on the fly through ``RowMap::xoff`` in csrc/passes.cuh; unpruned case)."""
+    b = np.asarray(chunk).reshape(world, zc, nyl, nk)
+    if cyclic:  # global ky row = yl * world + r
+        return np.ascontiguousarray(b.transpose(1, 2, 0, 3)).reshape(zc, nyl * world, nk)
+    return np.ascontiguousarray(b.transpose(1, 0, 2, 3)).reshape(zc, nyl * world, nk)
 
 
 def check_divisible(nz, ny, world):

@@ -95,6 +95,7 @@ class SimulBasePseudoSpectralB200:
         call("b2_set_aliasing", h, 1 if alias else 0)
         if self.ndim == 3:
             call("b2_set_no_vz_kz0", h, 1 if getattr(self, "no_vz_kz0", False) else 0)
+            call("b2_set_projection", h, int(getattr(self, "_projection_id", 0)))
 
     def mask_modified(self):
         """Call after editing ``oper.where_dealiased`` in place: the kept ranges of the pruned
@@ -152,8 +153,13 @@ class SimulNS3D(SimulBasePseudoSpectralB200):
         projection = getattr(self.params, "projection", None)
         if projection is None:
             self._projector = self.oper.project_perpk3d
-        elif projection in ("toroidal", "vortical", "poloidal"):
-            raise NotImplementedError(f"projection = {projection!r} is not implemented on the GPU path")
+            self._projection_id = 0
+        elif projection in ("toroidal", "vortical"):
+            self._projector = self.oper.project_toroidal
+            self._projection_id = 1
+        elif projection == "poloidal":
+            self._projector = self.oper.project_poloidal
+            self._projection_id = 2
         else:
             raise ValueError(f"No known projection for params.projection = {projection}")
 

@@ -67,6 +67,9 @@ int b2_divfft_from_vecfft(b2_plan* p, const double* vx, const double* vy, const 
                           double* div, void* stream);
 /* project_perpk3d: solvers/ns3d/solver.py:255-259 (in place) */
 int b2_project_perpk3d(b2_plan* p, double* vx, double* vy, double* vz, void* stream);
+/* project_toroidal / project_poloidal: operators/operators3d.py:911-958 / 788-856 (in place) */
+int b2_project_toroidal(b2_plan* p, double* vx, double* vy, double* vz, void* stream);
+int b2_project_poloidal(b2_plan* p, double* vx, double* vy, double* vz, void* stream);
 /* vector_product(a, b) -> written into b: solvers/ns3d/solver.py:226 */
 int b2_vector_product(const double* ax, const double* ay, const double* az, double* bx, double* by,
                       double* bz, long long n, void* stream);
@@ -134,6 +137,9 @@ int b2_sum(const double* x, long long n, double* out_dev, void* stream);
  * mask = where_dealiased (uint8, K-shaped, device; may be NULL = no dealiasing) */
 int b2_set_physics(b2_plan* p, int solver, double nu2, double nu4, double nu8, double num4, int has_f,
                    double f, double N, double beta, const uint8_t* mask);
+/* params.projection (solvers/ns3d/solver.py:139-174) used by the fused path for the tendencies and
+ * the end-of-step state: 0 None (project_perpk3d), 1 "toroidal" / "vortical", 2 "poloidal" */
+int b2_set_projection(b2_plan* p, int projection);
 /* params.no_vz_kz0 (solvers/ns3d/solver.py:135-137, 260-263): vz (and b) are zeroed at kz = 0
  * after every projection of the tendencies and of the end-of-step state */
 int b2_set_no_vz_kz0(b2_plan* p, int on);

@@ -245,7 +245,7 @@ def make_params(solver, nx, ny, nz=None, Lx=2 * np.pi, Ly=2 * np.pi, Lz=2 * np.p
     if solver.startswith("ns3d"):
         p.f = kw.pop("f", None)
         p.no_vz_kz0 = bool(kw.pop("no_vz_kz0", False))
-        p.projection = None
+        p.projection = kw.pop("projection", None)
     if solver in ("ns3d.strat", "ns3d.bouss"):
         p.N = kw.pop("N", 1.0)
     if solver == "ns2d":

@@ -95,11 +95,13 @@ class OracleSim:
         f=None,
         beta=0.0,
         no_vz_kz0=False,
+        projection=None,
     ):
         self.solver = solver
         self.nu_2, self.nu_4, self.nu_8, self.nu_m4 = nu_2, nu_4, nu_8, nu_m4
         self.N, self.f, self.beta = N, f, beta
         self.no_vz_kz0 = bool(no_vz_kz0)
+        self.projection = projection
         self.deltat = float(deltat0)
         self.scheme = type_time_scheme
         self.it = 0
@@ -195,15 +197,53 @@ class OracleSim:
 
     # ------------------------------------------------------------------ nonlinear terms
     def project_state_spect(self, state_spect):
-        """solvers/ns3d/solver.py:255-263 (projection=None)."""
-        self.oper.project_perpk3d(
-            state_spect.get_var("vx_fft"), state_spect.get_var("vy_fft"), state_spect.get_var("vz_fft")
-        )
+        """solvers/ns3d/solver.py:255-263 with params.projection (:158-174)."""
+        vx_fft, vy_fft, vz_fft = (state_spect.get_var(k) for k in ("vx_fft", "vy_fft", "vz_fft"))
+        if self.projection is None:
+            self.oper.project_perpk3d(vx_fft, vy_fft, vz_fft)
+        elif self.projection in ("toroidal", "vortical"):
+            self._project_toroidal(vx_fft, vy_fft, vz_fft)
+        elif self.projection == "poloidal":
+            self._project_poloidal(vx_fft, vy_fft, vz_fft)
+        else:
+            raise ValueError(f"No known projection for params.projection = {self.projection}")
         if self.no_vz_kz0:  # solver.py:260-263
             where_kz_0 = np.abs(self.oper.Kz) == 0.0
             state_spect.get_var("vz_fft")[where_kz_0] = 0.0
             if "b_fft" in state_spect.keys:
                 state_spect.get_var("b_fft")[where_kz_0] = 0.0
+
+    def _project_toroidal(self, vx_fft, vy_fft, vz_fft):
+        """operators/operators3d.py:911-958."""
+        oper = self.oper
+        Kh_square_nozero = oper.Kx**2 + oper.Ky**2
+        Kh_square_nozero[Kh_square_nozero == 0] = 1e-14
+        tmp = np.sqrt(1.0 / Kh_square_nozero)
+        cos_phi_k = oper.Kx * tmp
+        sin_phi_k = oper.Ky * tmp
+        tmp = -sin_phi_k * vx_fft + cos_phi_k * vy_fft
+        vx_fft[...] = -sin_phi_k * tmp
+        vy_fft[...] = cos_phi_k * tmp
+        vz_fft[...] = 0.0
+
+    def _project_poloidal(self, vx_fft, vy_fft, vz_fft):
+        """operators/operators3d.py:788-856."""
+        oper = self.oper
+        Kh_square = oper.Kx**2 + oper.Ky**2
+        K_square_nozero = Kh_square + oper.Kz**2
+        Kh_square_nozero = Kh_square.copy()
+        Kh_square_nozero[Kh_square_nozero == 0] = 1e-14
+        K_square_nozero[K_square_nozero == 0] = 1e-14
+        inv_Kh_square_nozero = 1.0 / Kh_square_nozero
+        inv_K_square_nozero = 1.0 / K_square_nozero
+        cos_theta_k = oper.Kz * np.sqrt(inv_K_square_nozero)
+        sin_theta_k = np.sqrt(Kh_square * inv_K_square_nozero)
+        cos_phi_k = oper.Kx * np.sqrt(inv_Kh_square_nozero)
+        sin_phi_k = oper.Ky * np.sqrt(inv_Kh_square_nozero)
+        tmp = cos_theta_k * cos_phi_k * vx_fft + cos_theta_k * sin_phi_k * vy_fft - sin_theta_k * vz_fft
+        vx_fft[...] = cos_theta_k * cos_phi_k * tmp
+        vy_fft[...] = cos_theta_k * sin_phi_k * tmp
+        vz_fft[...] = -sin_theta_k * tmp
 
     def dealiasing(self, thing):
         """operators3d.py:336-342; operators2d.py:200-220."""

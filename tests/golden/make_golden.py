@@ -40,6 +40,9 @@ CASES = {
     "bouss_16x16x16_rk4": ("ns3d.bouss", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2)),
     "ns3d_16x16x16_rk4_novzkz0": ("ns3d", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, no_vz_kz0=True)),
     "strat_16x16x8_rk2_novzkz0": ("ns3d.strat", (16, 16, 8), 4, dict(nu_4=1e-3, deltat0=1e-2, N=1.5, type_time_scheme="RK2", no_vz_kz0=True)),
+    "ns3d_16x16x16_rk4_toroidal": ("ns3d", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, projection="toroidal")),
+    "ns3d_16x12x8_rk2_poloidal": ("ns3d", (16, 12, 8), 4, dict(nu_2=1e-2, deltat0=1e-2, projection="poloidal", type_time_scheme="RK2", Lx=6.0)),
+    "strat_16x16x16_rk4_poloidal": ("ns3d.strat", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=2e-2, N=2.0, projection="poloidal")),
     # forced cases: a constant forcing_fft on the shell 2 <= |k|/dk <= 3.5 handed to the reference's
     # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
     "ns3d_16x16x16_rk4_forced": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),

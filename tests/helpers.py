@@ -68,7 +68,7 @@ def make_gpu_sim(meta, fused=None, mask=None):
     p.time_stepping.USE_CFL = False
     p.time_stepping.type_time_scheme = kw.pop("type_time_scheme", "RK4")
     p.time_stepping.deltat0 = kw.pop("deltat0", 1e-2)
-    for key in ("nu_2", "nu_4", "nu_8", "nu_m4", "f", "N", "beta", "no_vz_kz0"):
+    for key in ("nu_2", "nu_4", "nu_8", "nu_m4", "f", "N", "beta", "no_vz_kz0", "projection"):
         if key in kw:
             setattr(p, key, kw.pop(key))
     assert not kw, kw

@@ -59,12 +59,25 @@ def test_cyclic_distribution_balances_kept_rows():
     assert max(kept[True]) - min(kept[True]) <= 1            # cyclic: balanced
 
 
-def test_exchanged_row_is_a_permutation():
-    from fluidsim_b200.slab import exchanged_row
+def test_exchange_layout_is_a_bijection_and_unpacks_to_natural_order():
+    """exchange_index (K side, what SlabMapper computes) fills every slot of the send buffer once, and
+    natural_from_exchanged (what RowMap::xoff does on the receiving side) restores (zc, ny, nk)."""
+    from fluidsim_b200.slab import exchange_index, natural_from_exchanged
 
+    world, nyl, nzl, nk, nchunks = 4, 3, 4, 5, 2
+    ny, nz, zc = world * nyl, world * nzl, nzl // nchunks
+    yl, z, kx = np.meshgrid(np.arange(nyl), np.arange(nz), np.arange(nk), indexing="ij")
+    idx = exchange_index(z, kx, yl, nzl, nyl, nk, nchunks, ny)
+    assert sorted(idx.reshape(-1).tolist()) == list(range(nyl * nz * nk))
     for cyclic in (False, True):
-        rows = sorted(exchanged_row(i, 4, 8, cyclic) for i in range(32))
-        assert rows == list(range(32))
+        # a received chunk holding, at [r][zl][yl][kx], the global row that slot stands for
+        chunk = np.empty((world, zc, nyl, nk))
+        for r in range(world):
+            for y in range(nyl):
+                chunk[r, :, y, :] = (y * world + r) if cyclic else (r * nyl + y)
+        nat = natural_from_exchanged(chunk.reshape(-1), world, zc, nyl, nk, cyclic)
+        assert nat.shape == (zc, ny, nk)
+        assert np.array_equal(nat[0, :, 0], np.arange(ny))
 
 
 def test_bench_traffic_accounting():

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1, cyclic=False):
     """Distributed unnormalised inverse FFT of one field following the GPU phases' layouts."""
-    from fluidsim_b200.slab import exchange_index, exchanged_row
+    from fluidsim_b200.slab import exchange_index, natural_from_exchanged
 
     nyl, nzl, nk = ny // world, nz // world, nx // 2 + 1
     zc = nzl // nchunks
@@ -30,12 +30,11 @@ def _model_inverse_fft(k_loc, rank, world, nz, ny, nx, nchunks=1, cyclic=False):
     for c in range(nchunks):
         dist.all_to_all_single(torch.view_as_real(torch.from_numpy(recv[c * cs:(c + 1) * cs])).view(-1),
                                torch.view_as_real(torch.from_numpy(send[c * cs:(c + 1) * cs])).view(-1))
-        # phase B: the received chunk IS (ny, zc, nk); y-inverse then c2r along x
-        b = recv[c * cs:(c + 1) * cs].reshape(ny, zc, nk)
-        # rows arrive grouped by owning rank: bring them to natural ky order (RowMap on the GPU)
-        b = b[[exchanged_row(i, world, nyl, cyclic) for i in range(ny)]]
-        b = np.fft.ifft(b, axis=0) * ny
-        out[:, c * zc:(c + 1) * zc] = np.fft.irfft(b, n=nx, axis=2) * nx
+        # phase B: the received chunk is [rank][z in chunk][ky_loc][kx]; the y-inverse reads it through
+        # the row map and works on the natural (zc, ny, nk) array; then c2r along x
+        b = natural_from_exchanged(recv[c * cs:(c + 1) * cs], world, zc, nyl, nk, cyclic)
+        b = np.fft.ifft(b, axis=1) * ny
+        out[:, c * zc:(c + 1) * zc] = np.swapaxes(np.fft.irfft(b, n=nx, axis=2) * nx, 0, 1)
     return out  # (ny, nz_loc, nx)
 
 
