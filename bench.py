@@ -389,9 +389,17 @@ def own_arm(args):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (own arm) needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    # development: B2_BENCH_FORCE_SLAB=1 runs the slab (multi-GPU) code path on ONE rank, which makes
+    # its kernels profilable with ncu (never wrap a multi-rank command in ncu)
+    force_slab = world == 1 and os.environ.get("B2_BENCH_FORCE_SLAB", "0") not in ("0", "")
+    if world > 1 or force_slab:
         import datetime
 
+        if force_slab:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            os.environ.setdefault("RANK", "0")
+            os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
                                 timeout=datetime.timedelta(seconds=180))
     from fluidsim_b200 import _lib
@@ -400,7 +408,7 @@ def own_arm(args):
     # memory guard (single GPU): the fused path holds 12 (ns3d, aliased buffers) / 19 (strat) K fields
     # plus the mask; a grid that does not fit is an ERROR for the headline (no silent halving)
     size_note = None
-    if args.solver != "ns2d" and world == 1:  # (slab runs split the same grid: less memory per GPU)
+    if args.solver != "ns2d" and world == 1 and not force_slab:  # (slab runs split the same grid)
         free_b, _total_b = torch.cuda.mem_get_info()
         nfields = {"ns3d": 12, "ns3d.strat": 19}[args.solver]
         while args.n > 64:
@@ -415,7 +423,8 @@ def own_arm(args):
     parity = None
     if not args.no_parity:
         parity = parity_check(args, torch, world, rank)
-    if world > 1:
+    slab = world > 1 or force_slab
+    if slab:
         sim = make_slab_sim(args, torch, dist)
         ts = sim
         S = sim.state_spect
@@ -459,14 +468,14 @@ def own_arm(args):
 
     # kept fractions of the dealias-pruned transforms actually used in the timed steps
     kept = (1.0, 1.0, 1.0)
-    if world == 1 and sim.use_pruning and sim._fused_mask is not None:
+    if not slab and sim.use_pruning and sim._fused_mask is not None:
         import ctypes as C0
 
         bnd = (C0.c_int * 5)()
         _lib.lib.b2_get_pruning_bounds(sim.oper.plan.handle, bnd)
         n0, n1, nk = (1,) * (3 - ndim) + tuple(sim.oper.shapeK_loc)
         kept = (bnd[4] / nk, (bnd[2] + n1 - bnd[3]) / n1, (bnd[0] + n0 - bnd[1]) / n0)
-    elif world > 1 and sim.use_pruning and sim._prune is not None:
+    elif slab and sim.use_pruning and sim._prune is not None:
         keepx, kz_lo, kz_hi, _, _, gy_lo, gy_hi = sim._prune["args"]
         kept = (keepx / sim.nk, (gy_lo + sim.ny - gy_hi) / sim.ny, (kz_lo + sim.nz - kz_hi) / sim.nz)
 
@@ -545,7 +554,7 @@ def own_arm(args):
         t0 = time.perf_counter()
         for _ in range(ksteps):
             S.copy_(host, non_blocking=True)
-            if world == 1:
+            if not slab:
                 sim.state.mark_spect_modified()  # host data: the stepper re-checks that it is dealiased
             else:
                 sim.mark_spect_modified()
@@ -616,7 +625,7 @@ def own_arm(args):
                 "size_note": size_note,
                 "state_bytes_per_gpu": S.numel() * 16,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
-                "parallelism": "single GPU" if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all; lean buffers)",
+                "parallelism": ("single GPU" if not force_slab else "slab code path on ONE rank (diagnostic)") if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all; lean buffers)",
             },
             "nvlink": nvlink,
             "roofline": roofline,
@@ -636,7 +645,7 @@ def own_arm(args):
             "parity_check": parity,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if world > 1 or force_slab:
         dist.destroy_process_group()
 
 

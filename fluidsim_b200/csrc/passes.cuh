@@ -26,7 +26,8 @@ struct RowMap {
     int shift;  // log2 of the divisor (P if cyclic, nyl otherwise) when it is a power of two, else -1
     int lo[B2_MAXR], gap[B2_MAXR], nkr[B2_MAXR];
     long long blk[B2_MAXR];
-    // element offset (without the kx column) of logical row i, plane z of the chunk
+    // element offset (without the kx column) of logical row i, plane z of the chunk.  32-bit
+    // arithmetic inside a rank block (a chunk of one field stays far below 2^31 elements).
     B2_DEVINL long long xoff(int i, int z, int pitch) const {
         const int d = cyclic ? P : nyl;
         const int q = shift >= 0 ? (i >> shift) : i / d;
@@ -34,7 +35,7 @@ struct RowMap {
         const int r = cyclic ? m : q;
         const int yl = cyclic ? q : m;
         const int ylc = yl < lo[r] ? yl : yl - gap[r];
-        return blk[r] + ((long long)z * nkr[r] + ylc) * pitch;
+        return blk[r] + (long long)((unsigned)(z * nkr[r] + ylc) * (unsigned)pitch);
     }
 };
 

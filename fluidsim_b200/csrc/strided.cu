@@ -388,11 +388,14 @@ int b2i_first_inverse_pass(b2_plan* p, const cplx* const* in, cplx* const* out, 
 // index) and the kept kx columns are exchanged.
 struct SlabMapper {
     int nzl, nkl, pitch, y_lo, y_gap, zc;
+    int sh_nzl, sh_zc;  // log2 of nzl / zc when they are powers of two (-1 otherwise): no integer
+                        // divisions in front of the loads of the z-forward pass (measured: the
+                        // passes that LOAD through a mapper ran 1.45x slower per byte than plain ones)
     long long cstride;
     B2_DEVINL long long operator()(int z, int kx, int yl) const {
-        const int q = z / nzl;
+        const int q = sh_nzl >= 0 ? (z >> sh_nzl) : z / nzl;
         const int zl = z - q * nzl;
-        const int c = zl / zc;
+        const int c = sh_zc >= 0 ? (zl >> sh_zc) : zl / zc;
         const int zlc = zl - c * zc;
         const int ylc = yl < y_lo ? yl : yl - y_gap;
         return c * cstride + (((long long)q * zc + zlc) * nkl + ylc) * pitch + kx;
@@ -440,6 +443,14 @@ int b2i_slab_zpass(b2_plan* p, int dir, const cplx* const* in, cplx* const* out,
         map.nkl = p->n0; map.pitch = p->nk; map.y_lo = 1 << 30; map.y_gap = 0;
     }
     map.cstride = (long long)p->gy * map.zc * map.pitch;
+    auto log2_or_m1 = [](int v) {
+        if (v <= 0 || (v & (v - 1))) return -1;
+        int sh = 0;
+        while ((1 << sh) < v) ++sh;
+        return sh;
+    };
+    map.sh_nzl = log2_or_m1(map.nzl);
+    map.sh_zc = log2_or_m1(map.zc);
     if (g.nouter == 0) return 0;  // this rank owns only dealiased ky rows
     if (dir > 0) {
         PlainIn ld;
