@@ -97,6 +97,8 @@ def create_default_params(solver="ns3d"):
             max_elapsed=None,
         ),
     )
+    # pseudo_spect.py:159-167
+    p.time_stepping._set_child("phaseshift_random", dict(nb_pairs=1, nb_steps_compute_new_pair=None))
     # base/forcing/base.py:63-76, 189-196; specific.py:436-451, 777-786
     p._set_child(
         "forcing",

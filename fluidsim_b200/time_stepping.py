@@ -112,13 +112,31 @@ class TimeSteppingPseudoSpectralB200:
 
     def _init_time_scheme(self):
         type_time_scheme = self.params.time_stepping.type_time_scheme
-        if type_time_scheme == "RK2":
-            self._time_step_RK = self._time_step_RK2
-        elif type_time_scheme == "RK4":
-            self._time_step_RK = self._time_step_RK4
-        else:
+        # pseudo_spect.py:191-224.  RK2 / RK4 have the fused single-call path; the Euler, trapezoid and
+        # phase-shifting schemes are compositions of N() and elementwise updates on the same kernels
+        schemes = {
+            "RK2": self._time_step_RK2,
+            "RK4": self._time_step_RK4,
+            "Euler": self._time_step_Euler,
+            "Euler_phaseshift": self._time_step_Euler_phaseshift,
+            "Euler_phaseshift_random": self._time_step_Euler_phaseshift_random,
+            "RK2_trapezoid": self._time_step_RK2_trapezoid,
+            "RK2_phaseshift": self._time_step_RK2_phaseshift,
+            "RK2_phaseshift_random": self._time_step_RK2_phaseshift_random,
+            "RK2_phaseshift_exact": self._time_step_RK2_phaseshift_exact,
+        }
+        if type_time_scheme not in schemes:
             raise ValueError(f'Problem name time_scheme ("{type_time_scheme}")')
-        self._scheme_id = SCHEME_IDS[type_time_scheme]
+        self._time_step_RK = schemes[type_time_scheme]
+        self._scheme_id = SCHEME_IDS.get(type_time_scheme)
+        if self._scheme_id is None:
+            self._composed = self.fused  # N() through the fused kernels, the scheme composed here
+            self.fused = False
+        else:
+            self._composed = False
+        if type_time_scheme.endswith("_random"):
+            self._init_phaseshift_random()
+        self._phaseshift = None
         self._state_spect_tmp = None
         self._state_spect_tmp1 = None
 
@@ -237,6 +255,170 @@ class TimeSteppingPseudoSpectralB200:
             buf = SetOfVariables(like=self.sim.state.state_spect)
             setattr(self, name, buf)
         return buf
+
+    # ---- Euler / trapezoid / phase-shifting schemes (pseudo_spect.py:245-468, 519-796) -----------------
+    def _compute_tendencies(self, state_spect=None, old=None):
+        """N(state) -- through the fused kernels when the grid allows (arbitrary input: unpruned)."""
+        sim = self.sim
+        if self._composed:
+            return sim.tendencies_nonlin_fused(state_spect, old=old)
+        return sim.tendencies_nonlin(state_spect, old=old)
+
+    def _like_state(self, tensor):
+        return SetOfVariables(input_array=tensor, keys=self.sim.state.state_spect.keys, info="tmp")
+
+    def _get_phaseshift(self):
+        """pseudo_spect.py:281-300: exp(i/2 (dx Kx + dy Ky [+ dz Kz]))."""
+        if self._phaseshift is None:
+            oper = self.sim.oper
+            if self.sim.ndim == 2:
+                phase = 0.5 * (oper.deltax * oper.KX + oper.deltay * oper.KY)
+            else:
+                phase = 0.5 * (oper.deltax * oper.Kx + oper.deltay * oper.Ky + oper.deltaz * oper.Kz)
+            self._phaseshift = torch.exp(1j * phase)
+        return self._phaseshift
+
+    def _init_phaseshift_random(self):
+        """pseudo_spect.py:302-328."""
+        pp = self.params.time_stepping.phaseshift_random
+        if pp.nb_steps_compute_new_pair is None:
+            pp.nb_steps_compute_new_pair = 2 if pp.nb_pairs == 1 else 4 * pp.nb_pairs
+        self._index_phaseshift = 1
+        self._previous_index_pair = 0
+        self._previous_index_flip = 0
+        self._pairs_phaseshift = [self._new_random_pair() for _ in range(pp.nb_pairs)]
+
+    def _new_random_pair(self):
+        """oper.get_phases_random (operators3d.py:1128-1146, operators2d) + compute_phaseshift_terms."""
+        from random import uniform
+
+        oper = self.sim.oper
+        nd = self.sim.ndim
+        alphas = tuple(uniform(-0.5, 0.5) for _ in range(nd))
+        betas = tuple(a + 0.5 if a < 0 else a - 0.5 for a in alphas)
+        if nd == 3:
+            grids = (oper.deltax * oper.Kx, oper.deltay * oper.Ky, oper.deltaz * oper.Kz)
+        else:
+            grids = (oper.deltax * oper.KX, oper.deltay * oper.KY)
+        phase_alpha = sum(a * g for a, g in zip(alphas, grids))
+        phase_beta = sum(b * g for b, g in zip(betas, grids))
+        return torch.exp(1j * phase_alpha), torch.exp(1j * phase_beta)
+
+    def _get_phaseshift_random(self):
+        """pseudo_spect.py:330-372."""
+        from random import randint
+
+        pp = self.params.time_stepping.phaseshift_random
+        nb_pairs, nb_steps = pp.nb_pairs, pp.nb_steps_compute_new_pair
+        if nb_pairs == 1 and nb_steps == 1:
+            alpha, beta = self._pairs_phaseshift[0]
+        elif nb_pairs == 1 and nb_steps == 2:
+            pair = self._pairs_phaseshift[0]
+            alpha, beta = pair if self._index_phaseshift == 1 else pair[::-1]
+        else:
+            index_pair = randint(0, nb_pairs - 1)
+            pair = self._pairs_phaseshift[index_pair]
+            index_flip = randint(0, 1)
+            if index_pair == self._previous_index_pair and index_flip == self._previous_index_flip:
+                index_flip = 0 if index_flip else 1
+            self._previous_index_pair = index_pair
+            self._previous_index_flip = index_flip
+            alpha, beta = pair if index_flip else pair[::-1]
+        if self._index_phaseshift == nb_steps:
+            self._index_phaseshift = 1
+            self._pairs_phaseshift.pop(0)
+            self._pairs_phaseshift.append(self._new_random_pair())
+        else:
+            self._index_phaseshift += 1
+        return alpha, beta
+
+    def _shifted_tendencies(self, phaseshift, state_tensor):
+        """N(phaseshift * S) / phaseshift as a tensor."""
+        shifted = self._like_state(phaseshift * state_tensor)
+        return self._compute_tendencies(shifted).tensor / phaseshift
+
+    def _euler_inplace(self, tendencies_tensor, diss):
+        """step_Euler_inplace (pseudo_spect.py:59-61)."""
+        S = self.sim.state.state_spect
+        t = tendencies_tensor.contiguous()
+        call("b2_step_euler", self.sim.oper.plan.handle, ptr(S.tensor), self.deltat, ptr(t), ptr(diss),
+             ptr(S.tensor), S.nvar, stream_ptr())
+
+    def _time_step_Euler(self):
+        diss = self.exact_linear_coefs.get_updated_coefs()[0]
+        self._euler_inplace(self._compute_tendencies().tensor, diss)
+
+    def _time_step_Euler_phaseshift(self):
+        diss = self.exact_linear_coefs.get_updated_coefs()[0]
+        S = self.sim.state.state_spect.tensor
+        tendencies_0 = self._compute_tendencies().tensor
+        tendencies_shifted = self._shifted_tendencies(self._get_phaseshift(), S)
+        self._euler_inplace(0.5 * (tendencies_0 + tendencies_shifted), diss)
+
+    def _time_step_Euler_phaseshift_random(self):
+        diss = self.exact_linear_coefs.get_updated_coefs()[0]
+        S = self.sim.state.state_spect.tensor
+        alpha, beta = self._get_phaseshift_random()
+        t_alpha = self._shifted_tendencies(alpha, S)
+        t_beta = self._shifted_tendencies(beta, S)
+        self._euler_inplace(0.5 * (t_alpha + t_beta), diss)
+
+    def _rk2_first_half(self, tendencies_0, diss):
+        """state_spect_1 = step_Euler(state_spect, dt, tendencies_0, diss)."""
+        sim = self.sim
+        S = sim.state.state_spect
+        state_spect_1 = self._tmp_like_state("_state_spect_tmp")
+        call("b2_step_euler", sim.oper.plan.handle, ptr(S.tensor), self.deltat, ptr(tendencies_0.contiguous()),
+             ptr(diss), ptr(state_spect_1.tensor), S.nvar, stream_ptr())
+        return state_spect_1
+
+    def _step_like_rk2(self, tendencies_d, diss, diss2):
+        S = self.sim.state.state_spect
+        call("b2_step_like_rk2", self.sim.oper.plan.handle, ptr(S.tensor), self.deltat,
+             ptr(tendencies_d.contiguous()), ptr(diss), ptr(diss2), S.nvar, stream_ptr())
+
+    def _time_step_RK2_trapezoid(self):
+        dt = self.deltat
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        S = self.sim.state.state_spect.tensor
+        tendencies_0 = self._compute_tendencies().tensor.clone()
+        state_spect_1 = self._rk2_first_half(tendencies_0, diss)
+        tendencies_1 = self._compute_tendencies(state_spect_1).tensor
+        S.copy_((S + dt / 2 * tendencies_0) * diss + dt / 2 * tendencies_1)
+
+    def _time_step_RK2_phaseshift(self):
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        tendencies_0 = self._compute_tendencies().tensor.clone()
+        state_spect_1 = self._rk2_first_half(tendencies_0, diss)
+        phaseshift = self._get_phaseshift()
+        tendencies_1_shift = self._compute_tendencies(self._like_state(phaseshift * state_spect_1.tensor)).tensor
+        tendencies_d = 0.5 * (tendencies_0 + tendencies_1_shift / phaseshift)
+        self._step_like_rk2(tendencies_d, diss, diss2)
+
+    def _time_step_RK2_phaseshift_random(self):
+        """pseudo_spect.py:640-733."""
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        S = self.sim.state.state_spect.tensor
+        alpha, beta = self._get_phaseshift_random()
+        tendencies_0 = self._shifted_tendencies(alpha, S)
+        state_spect_1 = self._rk2_first_half(tendencies_0, diss)
+        tendencies_1 = self._shifted_tendencies(beta, state_spect_1.tensor)
+        tendencies_d = 0.5 * (tendencies_0 + tendencies_1)
+        self._step_like_rk2(tendencies_d, diss, diss2)
+
+    def _time_step_RK2_phaseshift_exact(self):
+        """pseudo_spect.py:735-796."""
+        diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
+        S = self.sim.state.state_spect.tensor
+        phaseshift = self._get_phaseshift()
+        tendencies_0 = self._compute_tendencies().tensor.clone()
+        tendencies_0_shift = self._compute_tendencies(self._like_state(phaseshift * S)).tensor
+        tendencies_d0 = 0.5 * (tendencies_0 + tendencies_0_shift / phaseshift)
+        state_spect_1 = self._rk2_first_half(tendencies_d0, diss)
+        tendencies_1 = self._compute_tendencies(state_spect_1).tensor.clone()
+        tendencies_1_shift = self._compute_tendencies(self._like_state(phaseshift * state_spect_1.tensor)).tensor
+        tendencies_d = 0.5 * (tendencies_d0 + 0.5 * (tendencies_1 + tendencies_1_shift / phaseshift))
+        self._step_like_rk2(tendencies_d, diss, diss2)
 
     def _time_step_RK2(self):
         dt = self.deltat

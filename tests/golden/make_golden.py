@@ -43,6 +43,16 @@ CASES = {
     "ns3d_16x16x16_rk4_toroidal": ("ns3d", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, projection="toroidal")),
     "ns3d_16x12x8_rk2_poloidal": ("ns3d", (16, 12, 8), 4, dict(nu_2=1e-2, deltat0=1e-2, projection="poloidal", type_time_scheme="RK2", Lx=6.0)),
     "strat_16x16x16_rk4_poloidal": ("ns3d.strat", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=2e-2, N=2.0, projection="poloidal")),
+    # f-4: the other time schemes of TimeSteppingPseudoSpectral (pseudo_spect.py:245-796); the *_random
+    # ones draw from Python's `random` (seeded with `random_seed` right before the objects are built)
+    "ns3d_16x16x16_euler": ("ns3d", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=5e-3, type_time_scheme="Euler")),
+    "ns3d_16x16x16_euler_phaseshift": ("ns3d", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=5e-3, type_time_scheme="Euler_phaseshift")),
+    "ns3d_16x12x8_rk2_trapezoid": ("ns3d", (16, 12, 8), 3, dict(nu_2=1e-2, deltat0=1e-2, type_time_scheme="RK2_trapezoid", Lx=6.0)),
+    "ns3d_16x16x16_rk2_phaseshift": ("ns3d", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=1e-2, type_time_scheme="RK2_phaseshift")),
+    "strat_16x16x16_rk2_phaseshift_exact": ("ns3d.strat", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=1e-2, N=2.0, type_time_scheme="RK2_phaseshift_exact")),
+    "ns2d_32x32_rk2_phaseshift": ("ns2d", (32, 32), 4, dict(nu_8=1e-8, deltat0=1e-2, Lx=8.0, Ly=8.0, type_time_scheme="RK2_phaseshift")),
+    "ns3d_16x16x16_rk2_phaseshift_random": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=1e-2, type_time_scheme="RK2_phaseshift_random", random_seed=11)),
+    "ns2d_32x32_euler_phaseshift_random": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=5e-3, Lx=8.0, Ly=8.0, type_time_scheme="Euler_phaseshift_random", random_seed=5)),
     # forced cases: a constant forcing_fft on the shell 2 <= |k|/dk <= 3.5 handed to the reference's
     # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
     "ns3d_16x16x16_rk4_forced": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),
@@ -89,10 +99,20 @@ def main():
         nz = shape[2] if len(shape) == 3 else None
         # initial condition: the reference's noise recipe (restated in step_np.init_noise, which
         # is itself checked against the reference in tests/test_oracle.py)
-        o = step_np.OracleSim(solver, nx, ny, nz, **kw)
+        kw = dict(kw)
+        random_seed = kw.pop("random_seed", None)
+        scheme = kw.get("type_time_scheme", "RK4")
+        okw = dict(kw)
+        if scheme not in ("RK2", "RK4"):
+            okw["type_time_scheme"] = "RK4"  # the oracle only provides the initial state here
+        o = step_np.OracleSim(solver, nx, ny, nz, **okw)
         o.init_noise()
         s0 = np.array(o.state_spect)
         params = refshim.make_params(solver, nx, ny, nz, **kw)
+        if random_seed is not None:
+            import random
+
+            random.seed(random_seed)
         ref = refshim.RefSim(solver, params)
         ref.set_state_spect(s0)
         extra = {}
@@ -109,11 +129,12 @@ def main():
         states = []
         for _ in range(nsteps):
             states.append(ref.step())
-        e = step_np.OracleSim(solver, nx, ny, nz, **kw)
+        e = step_np.OracleSim(solver, nx, ny, nz, **okw)
         e.set_state_spect(states[-1])
         np.savez_compressed(
             os.path.join(outdir, name + ".npz"),
-            meta=json.dumps(dict(solver=solver, shape=shape, nsteps=nsteps, params=kw)),
+            meta=json.dumps(dict(solver=solver, shape=shape, nsteps=nsteps, params=kw,
+                                 **({} if random_seed is None else {"random_seed": random_seed}))),
             state0=s0,
             mask=mask,
             tend0=tend0,

@@ -33,12 +33,21 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+ORACLE_SCHEMES = ("RK2", "RK4")
+
+
 def make_oracle(meta):
+    """Numpy oracle for a golden / test case.  The oracle restates RK2 and RK4 only; for goldens of
+    the other schemes (made by the reference's own time stepper) it still provides operators,
+    tendencies and observables, built with RK4."""
     from oracle import step_np
 
     shape = meta["shape"]
     nz = shape[2] if len(shape) == 3 else None
-    return step_np.OracleSim(meta["solver"], shape[0], shape[1], nz, **meta["params"])
+    kw = dict(meta["params"])
+    if kw.get("type_time_scheme", "RK4") not in ORACLE_SCHEMES:
+        kw["type_time_scheme"] = "RK4"
+    return step_np.OracleSim(meta["solver"], shape[0], shape[1], nz, **kw)
 
 
 def make_gpu_sim(meta, fused=None, mask=None):
@@ -72,6 +81,10 @@ def make_gpu_sim(meta, fused=None, mask=None):
         if key in kw:
             setattr(p, key, kw.pop(key))
     assert not kw, kw
+    if "random_seed" in meta:  # *_random schemes draw from Python's `random` like the reference
+        import random
+
+        random.seed(meta["random_seed"])
     sim = cls(p, fused=fused)
     if mask is not None:
         # the dealiasing mask is an INPUT of the CUDA path (cubic comparator is [EXT] unpinned)
