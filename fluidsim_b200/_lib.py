@@ -49,6 +49,7 @@ SIGNATURES = {
     "b2_gradfft_from_fft2d": [_p, _p, _p, _p, _p],
     "b2_rotfft_from_vecfft2d": [_p, _p, _p, _p, _p],
     "b2_compute_frot": [_p, _p, _p, _p, _d, _p, _ll, _p],
+    "b2_tendencies_ns2d_buoyancy": [_p, _p, _p, _p, _p, _p, _d, _i, _p, _p, _ll, _p],
     "b2_compute_fb_fft": [_p, _d, _p, _ll, _p],
     "b2_add_inplace": [_p, _p, _ll, _p],
     "b2_exact_coefs": [_p, _d, _d, _d, _d, _d, _p, _p, _p],

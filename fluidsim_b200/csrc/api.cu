@@ -421,6 +421,19 @@ __global__ void frot_kernel(const double* ux, const double* uy, const double* px
     o[i] = beta == 0.0 ? -ux[i] * px[i] - uy[i] * py[i] : -ux[i] * px[i] - uy[i] * (py[i] + beta);
 }
 
+// tendencies_nonlin_ns2dstrat / _ns2dbouss (solvers/ns2d/strat/solver.py:21-27, bouss/solver.py:21-27)
+__global__ void ns2d_buoyancy_kernel(const double* ux, const double* uy, const double* px_rot,
+                                     const double* py_rot, const double* px_b, const double* py_b, double N2,
+                                     int bouss, double* f_rot, double* f_b, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double u = ux[i], v = uy[i], pxb = px_b[i], pyb = py_b[i];
+    const double adv_rot = -u * px_rot[i] - v * py_rot[i];
+    const double adv_b = -u * pxb - v * pyb;
+    f_rot[i] = bouss ? adv_rot + pxb : adv_rot;
+    f_b[i] = bouss ? adv_b : adv_b - N2 * v;
+}
+
 __global__ void fb_kernel(cplx* d, double N2, const cplx* vz, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -550,6 +563,15 @@ extern "C" int b2_compute_frot(const double* ux, const double* uy, const double*
                                double beta, double* out, long long n, void* stream) {
     frot_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(ux, uy, px, py, beta, out, n);
     B2_LAUNCH_CHECK("frot_kernel");
+    return 0;
+}
+extern "C" int b2_tendencies_ns2d_buoyancy(const double* ux, const double* uy, const double* px_rot,
+                                          const double* py_rot, const double* px_b, const double* py_b,
+                                          double N, int bouss, double* f_rot, double* f_b, long long n,
+                                          void* stream) {
+    ns2d_buoyancy_kernel<<<B2_1D_GRID(n), 0, (cudaStream_t)stream>>>(ux, uy, px_rot, py_rot, px_b, py_b, N * N,
+                                                                     bouss, f_rot, f_b, n);
+    B2_LAUNCH_CHECK("ns2d_buoyancy_kernel");
     return 0;
 }
 extern "C" int b2_compute_fb_fft(double* div_vb, double N, const double* vz, long long nk, void* stream) {

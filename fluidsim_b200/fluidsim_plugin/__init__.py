@@ -2,7 +2,10 @@
 
     fluidsim.solvers.ns3d : b200       -> fluidsim_b200.fluidsim_plugin.ns3d        (key "ns3d.b200")
     fluidsim.solvers.ns3d : strat.b200 -> fluidsim_b200.fluidsim_plugin.ns3d_strat  (key "ns3d.strat.b200")
+    fluidsim.solvers.ns3d : bouss.b200 -> fluidsim_b200.fluidsim_plugin.ns3d_bouss  (key "ns3d.bouss.b200")
     fluidsim.solvers.ns2d : b200       -> fluidsim_b200.fluidsim_plugin.ns2d        (key "ns2d.b200")
+    fluidsim.solvers.ns2d : strat.b200 -> fluidsim_b200.fluidsim_plugin.ns2d_strat  (key "ns2d.strat.b200")
+    fluidsim.solvers.ns2d : bouss.b200 -> fluidsim_b200.fluidsim_plugin.ns2d_bouss  (key "ns2d.bouss.b200")
 
 fluidsim resolves a solver key to such a module and takes its ``Simul`` class
 (``/root/reference/lib/fluidsim_core/loader.py:17-74``, ``fluidsim/util/util.py:75-106``); the class

@@ -65,7 +65,7 @@ def create_default_params(solver="ns3d"):
         p.projection = None
         if solver == "ns3d.strat":
             p.N = 1.0
-    elif solver == "ns2d":
+    elif solver in ("ns2d", "ns2d.strat", "ns2d.bouss"):
         p._set_child(
             "oper",
             dict(
@@ -81,6 +81,8 @@ def create_default_params(solver="ns3d"):
             ),
         )
         p.beta = 0.0
+        if solver == "ns2d.strat":  # ns2d/strat/solver.py:65-69
+            p.N = 1.0
     else:
         raise ValueError(f"unknown solver {solver!r}")
     p._set_child(

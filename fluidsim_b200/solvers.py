@@ -1,4 +1,4 @@
-"""GPU ``Simul`` classes for ns3d, ns3d.strat and ns2d.
+"""GPU ``Simul`` classes for ns3d, ns3d.strat, ns3d.bouss, ns2d, ns2d.strat and ns2d.bouss.
 
 Host-side mirror of ``/root/reference/fluidsim/solvers/ns3d/solver.py:57-263``,
 ``solvers/ns3d/strat/solver.py:57-216`` and ``solvers/ns2d/solver.py:73-194`` reduced to the hot
@@ -15,13 +15,15 @@ from ._lib import SOLVER_IDS, call, lib, ptr, stream_ptr
 from .operators import OperatorsPseudoSpectral2D, OperatorsPseudoSpectral3D, vector_product
 from .params import create_default_params
 from .setofvariables import SetOfVariables
-from .state import StateNS2D, StateNS3D, StateNS3DStrat
+from .state import StateNS2D, StateNS2DStrat, StateNS3D, StateNS3DStrat
 from .time_stepping import TimeSteppingPseudoSpectralB200
 
 
 class SimulBasePseudoSpectralB200:
     short_name = None
     ndim = 3
+    # False: the solver runs on the operator-level kernels only (no fused b2_time_step / b2_tendencies)
+    supports_fused = True
     Operators = OperatorsPseudoSpectral3D
     State = StateNS3D
     TimeStepping = TimeSteppingPseudoSpectralB200
@@ -317,7 +319,77 @@ class SimulNS2D(SimulBasePseudoSpectralB200):
         return tendencies_fft
 
 
-SIMUL_CLASSES = {"ns3d": SimulNS3D, "ns3d.strat": SimulNS3DStrat, "ns3d.bouss": SimulNS3DBouss, "ns2d": SimulNS2D}
+class SimulNS2DStrat(SimulNS2D):
+    """solvers/ns2d/strat/solver.py:59-181 -- state (rot_fft, b_fft); runs on the operator-level kernels
+    (FFT passes, gradfft / vecfft, one elementwise product kernel)."""
+
+    short_name = "ns2d.strat"
+    State = StateNS2DStrat
+    supports_fused = False
+    _bouss = 0
+
+    @property
+    def fields_tmp(self):
+        if self._fields_tmp is None:  # field_tmp0..5 of ns2d/state.py:43-46 + strat/state.py:50-54
+            self._fields_tmp = tuple(self.oper.create_arrayX() for _ in range(6))
+        return self._fields_tmp
+
+    def tendencies_nonlin(self, state_spect=None, old=None):
+        """strat/solver.py:71-181 (bouss/solver.py:65-173 with ``_bouss``)."""
+        oper = self.oper
+        ifft_as_arg = oper.ifft_as_arg
+        ifft_as_arg_destroy = oper.oper_fft.ifft_as_arg_destroy
+        fft_as_arg = oper.fft_as_arg
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state.state_spect)
+        else:
+            tendencies_fft = old
+        f_rot_fft = tendencies_fft.get_var("rot_fft")
+        f_b_fft = tendencies_fft.get_var("b_fft")
+        if state_spect is None:
+            rot_fft = self.state.state_spect.tensor[0]
+            b_fft = self.state.state_spect.tensor[1]
+            ux = self.state.state_phys.get_var("ux")
+            uy = self.state.state_phys.get_var("uy")
+        else:
+            rot_fft = state_spect.get_var("rot_fft")
+            b_fft = state_spect.get_var("b_fft")
+            ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
+            ux, uy = self.fields_tmp[0:2]
+            ifft_as_arg_destroy(ux_fft, ux)
+            ifft_as_arg_destroy(uy_fft, uy)
+        px_rot_fft, py_rot_fft = oper.gradfft_from_fft(rot_fft)
+        px_b_fft, py_b_fft = oper.gradfft_from_fft(b_fft)
+        px_rot, py_rot, px_b, py_b = self.fields_tmp[2:6]
+        ifft_as_arg_destroy(px_rot_fft, px_rot)
+        ifft_as_arg_destroy(py_rot_fft, py_rot)
+        ifft_as_arg(px_b_fft, px_b)  # px_b_fft is used again below
+        ifft_as_arg_destroy(py_b_fft, py_b)
+        # f_rot in px_rot's buffer, f_b in py_rot's (px_b is an input of both expressions)
+        call("b2_tendencies_ns2d_buoyancy", ptr(ux), ptr(uy), ptr(px_rot), ptr(py_rot), ptr(px_b), ptr(py_b),
+             float(getattr(self.params, "N", 0.0)), int(self._bouss), ptr(px_rot), ptr(py_rot), px_rot.numel(),
+             stream_ptr())
+        fft_as_arg(py_rot, f_b_fft)
+        fft_as_arg(px_rot, f_rot_fft)
+        if not self._bouss:  # strat/solver.py:156
+            call("b2_add_inplace", ptr(f_rot_fft), ptr(px_b_fft), f_rot_fft.numel(), stream_ptr())
+        oper.dealiasing(tendencies_fft)
+        if self.params.forcing.enable:
+            tendencies_fft += self.forcing.get_forcing()
+        return tendencies_fft
+
+
+class SimulNS2DBouss(SimulNS2DStrat):
+    """solvers/ns2d/bouss/solver.py:60-173."""
+
+    short_name = "ns2d.bouss"
+    _bouss = 1
+
+
+SIMUL_CLASSES = {
+    "ns3d": SimulNS3D, "ns3d.strat": SimulNS3DStrat, "ns3d.bouss": SimulNS3DBouss,
+    "ns2d": SimulNS2D, "ns2d.strat": SimulNS2DStrat, "ns2d.bouss": SimulNS2DBouss,
+}
 
 
 def make_simul(solver, params, fused=None):

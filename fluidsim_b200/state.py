@@ -162,3 +162,35 @@ class StateNS2D(StatePseudoSpectral):
         oper = self.oper
         rot_fft = self.state_spect.tensor[0]
         return oper.sum_wavenumbers(0.5 * rot_fft.abs() ** 2 / oper.K2_not0)
+
+
+class StateNS2DStrat(StateNS2D):
+    """solvers/ns2d/strat/state.py:19-163 and solvers/ns2d/bouss/state.py:19-122 (same state)."""
+
+    keys_state_phys = ("ux", "uy", "rot", "b")
+    keys_state_spect = ("rot_fft", "b_fft")
+
+    def _statephys_from_statespect(self):
+        """ns2d/strat/state.py:137-151."""
+        super()._statephys_from_statespect()
+        self.oper.ifft_as_arg(self.state_spect.tensor[1], self._state_phys.get_var("b"))
+
+    def statespect_from_statephys(self):
+        """ns2d/strat/state.py:153-163."""
+        phys = self.state_phys if self._state_phys is None else self._state_phys
+        self.oper.fft_as_arg(phys.get_var("rot"), self.state_spect.tensor[0])
+        self.oper.fft_as_arg(phys.get_var("b"), self.state_spect.tensor[1])
+        self._phys_dirty = False
+        self.sim._state_dealiased = False
+
+    def init_from_rotbfft(self, rot_fft, b_fft):
+        """ns2d/strat/state.py:165-173."""
+        self.oper.dealiasing(rot_fft)
+        self.oper.dealiasing(b_fft)
+        self.state_spect.set_var("rot_fft", rot_fft)
+        self.state_spect.set_var("b_fft", b_fft)
+        self.statephys_from_statespect()
+
+    def init_from_rotfft(self, rot_fft):
+        """ns2d/strat/state.py:233-236."""
+        self.init_from_rotbfft(rot_fft, self.oper.create_arrayK(value=0.0))

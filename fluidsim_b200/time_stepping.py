@@ -71,9 +71,12 @@ class TimeSteppingPseudoSpectralB200:
             signal.signal(signal.SIGUSR2, self._handler_signals)
         except (ValueError, AttributeError):
             warn("Cannot handle signals - is multithreading on?")
-        self.fused = sim.oper.plan.is_fast if fused is None else bool(fused)
+        can_fuse = sim.oper.plan.is_fast and getattr(sim, "supports_fused", True)
+        self.fused = can_fuse if fused is None else bool(fused)
         if self.fused and not sim.oper.plan.is_fast:
             raise ValueError("fused time stepping needs power-of-two grid sizes in [8, 2048]")
+        if self.fused and not can_fuse:
+            raise ValueError(f"solver {sim.short_name} runs on the operator-level kernels only (fused=False)")
         self.init_from_params()
 
     def _handler_signals(self, signal_number, stack):

@@ -84,6 +84,14 @@ int b2_gradfft_from_fft2d(b2_plan* p, const double* f, double* px, double* py, v
 int b2_rotfft_from_vecfft2d(b2_plan* p, const double* ux, const double* uy, double* rot, void* stream);
 int b2_compute_frot(const double* ux, const double* uy, const double* px, const double* py, double beta,
                     double* out, long long n, void* stream);
+/* tendencies_nonlin_ns2dstrat (solvers/ns2d/strat/solver.py:21-27; bouss = 0):
+ *   f_rot = -ux px_rot - uy py_rot ; f_b = -ux px_b - uy py_b - N^2 uy
+ * tendencies_nonlin_ns2dbouss (solvers/ns2d/bouss/solver.py:21-27; bouss = 1):
+ *   f_rot = -ux px_rot - uy py_rot + px_b ; f_b = -ux px_b - uy py_b
+ * real physical-space fields of n points; the outputs may alias px_rot / px_b */
+int b2_tendencies_ns2d_buoyancy(const double* ux, const double* uy, const double* px_rot, const double* py_rot,
+                                const double* px_b, const double* py_b, double N, int bouss, double* f_rot,
+                                double* f_b, long long n, void* stream);
 /* compute_fb_fft: solvers/ns3d/strat/solver.py:29-33 : fb = -div_vb - N^2 vz (in place in div_vb) */
 int b2_compute_fb_fft(double* div_vb, double N, const double* vz, long long nk, void* stream);
 /* a += b (complex arrays of nk elements): `fz_fft += b_fft`, strat/solver.py:198 */

@@ -250,15 +250,18 @@ def make_params(solver, nx, ny, nz=None, Lx=2 * np.pi, Ly=2 * np.pi, Lz=2 * np.p
         p.projection = kw.pop("projection", None)
     if solver in ("ns3d.strat", "ns3d.bouss"):
         p.N = kw.pop("N", 1.0)
-    if solver == "ns2d":
+    if solver.startswith("ns2d"):
         p.beta = kw.pop("beta", 0.0)
+    if solver == "ns2d.strat":  # ns2d/strat/solver.py:65-69
+        p.N = kw.pop("N", 1.0)
     if kw:
         raise TypeError(f"unknown params {sorted(kw)}")
     return p
 
 
 class RefSim:
-    """Wire the reference's own classes for one solver (ns3d | ns3d.strat | ns2d).
+    """Wire the reference's own classes for one solver (ns3d | ns3d.strat | ns3d.bouss | ns2d |
+    ns2d.strat | ns2d.bouss).
 
     Mirrors ``SimulBase.__init__`` (``base/solvers/base.py:117-223``): Operators ->
     State -> TimeStepping, then fields are set by the caller with ``set_state_spect``.
@@ -272,7 +275,7 @@ class RefSim:
 
         self.solver = solver
         self.params = params
-        if solver == "ns2d":
+        if solver.startswith("ns2d"):
             from fluidsim.operators.operators2d import OperatorsPseudoSpectral2D as Oper
         else:
             from fluidsim.operators.operators3d import OperatorsPseudoSpectral3D as Oper
@@ -295,6 +298,10 @@ class RefSim:
                 "TimeSteppingPseudoSpectralNS3D",
             ),
             "ns2d": ("ns2d.state", "StateNS2D", None, None),
+            # ns2d.strat has its own time-stepping class, but it only changes the CFL rule
+            # (ns2d/strat/time_stepping.py:31-110), which the shim does not run
+            "ns2d.strat": ("ns2d.strat.state", "StateNS2DStrat", None, None),
+            "ns2d.bouss": ("ns2d.bouss.state", "StateNS2DBouss", None, None),
         }[solver]
         State = getattr(importlib.import_module("fluidsim.solvers." + statemod), statecls)
         if tsmod is None:

@@ -67,7 +67,8 @@ def step_like_RK2(state_spect, dt, tendencies, diss, diss2):
 
 
 class OracleSim:
-    """ns3d | ns3d.strat | ns2d simulation object reduced to its hot path.
+    """ns3d | ns3d.strat | ns3d.bouss | ns2d | ns2d.strat | ns2d.bouss simulation object reduced to
+    its hot path.
 
     Mirrors the construction order of ``base/solvers/base.py:117-223`` and the per-step
     sequence of ``solvers/ns3d/time_stepping.py:8-20`` /
@@ -109,12 +110,16 @@ class OracleSim:
         # forcing_fft of the current step (same shape as state_spect) or None; the reference adds
         # `self.forcing.get_forcing()` to the tendencies (solvers/ns3d/solver.py:243-244)
         self.forcing_fft = None
-        if solver == "ns2d":
+        if solver in ("ns2d", "ns2d.strat", "ns2d.bouss"):
             self.ndim = 2
             self.oper = OperatorsPseudoSpectral2D(nx, ny, Lx, Ly, coef_dealiasing=coef_dealiasing)
             self.oper.Lx, self.oper.Ly = self.oper.lx, self.oper.ly
-            keys_spect = ["rot_fft"]
-            keys_phys = ["ux", "uy", "rot"]
+            if solver == "ns2d":
+                keys_spect = ["rot_fft"]
+                keys_phys = ["ux", "uy", "rot"]
+            else:  # ns2d/strat/state.py:27-47, ns2d/bouss/state.py:27-38
+                keys_spect = ["rot_fft", "b_fft"]
+                keys_phys = ["ux", "uy", "rot", "b"]
         elif solver in ("ns3d", "ns3d.strat", "ns3d.bouss"):
             self.ndim = 3
             self.oper = OperatorsPseudoSpectral3D(
@@ -135,7 +140,8 @@ class OracleSim:
         )
         self.state_spect[:] = 0
         self.state_phys[:] = 0
-        n_tmp = 4 if self.ndim == 2 else 6  # ns2d/state.py:43-46, ns3d/state.py:46-52
+        # ns2d/state.py:43-46 (+ field_tmp4/5 of ns2d/strat/state.py:50-54), ns3d/state.py:46-52
+        n_tmp = 6 if self.ndim == 3 or solver != "ns2d" else 4
         self.fields_tmp = tuple(np.empty(oper.shapeX_loc) for _ in range(n_tmp))
         self.fields_spect_tmp = tuple(
             np.empty(oper.shapeK_loc, dtype=np.complex128) for _ in range(3)
@@ -187,6 +193,8 @@ class OracleSim:
             oper.ifft_as_arg(rot_fft, self.state_phys.get_var("rot"))
             oper.ifft_as_arg(ux_fft, self.state_phys.get_var("ux"))
             oper.ifft_as_arg(uy_fft, self.state_phys.get_var("uy"))
+            if self.solver != "ns2d":  # ns2d/strat/state.py:137-151, ns2d/bouss/state.py:96-110
+                oper.ifft_as_arg(self.state_spect.get_var("b_fft"), self.state_phys.get_var("b"))
         else:
             for ik in range(self.state_spect.nvar):
                 oper.ifft_as_arg(self.state_spect[ik].view(np.ndarray), self.state_phys[ik].view(np.ndarray))
@@ -258,6 +266,8 @@ class OracleSim:
     def tendencies_nonlin(self, state_spect=None, old=None):
         if self.solver == "ns2d":
             return self._tendencies_ns2d(state_spect, old)
+        if self.ndim == 2:
+            return self._tendencies_ns2d_buoyancy(state_spect, old)
         return self._tendencies_ns3d(state_spect, old)
 
     def _tendencies_ns3d(self, state_spect=None, old=None):
@@ -341,6 +351,50 @@ class OracleSim:
         oper.fft_as_arg(Frot, Frot_fft)
         self.dealiasing(Frot_fft)
         if self.forcing_fft is not None:  # solvers/ns2d/solver.py:190-191 (after the dealiasing)
+            tendencies_fft += self.forcing_fft
+        return tendencies_fft
+
+    def _tendencies_ns2d_buoyancy(self, state_spect=None, old=None):
+        """solvers/ns2d/strat/solver.py:71-181 (tendencies_nonlin_ns2dstrat :21-27) and
+        solvers/ns2d/bouss/solver.py:65-173 (tendencies_nonlin_ns2dbouss :21-27)."""
+        oper = self.oper
+        if old is None:
+            tendencies_fft = SetOfVariables(like=self.state_spect)
+        else:
+            tendencies_fft = old
+        f_rot_fft = tendencies_fft.get_var("rot_fft")
+        f_b_fft = tendencies_fft.get_var("b_fft")
+        if state_spect is None:
+            rot_fft = self.state_spect.get_var("rot_fft")
+            b_fft = self.state_spect.get_var("b_fft")
+            ux = self.state_phys.get_var("ux")
+            uy = self.state_phys.get_var("uy")
+        else:
+            rot_fft = state_spect.get_var("rot_fft")
+            b_fft = state_spect.get_var("b_fft")
+            ux_fft, uy_fft = oper.vecfft_from_rotfft(rot_fft)
+            ux, uy = self.fields_tmp[0:2]
+            oper.ifft_as_arg(ux_fft, ux)
+            oper.ifft_as_arg(uy_fft, uy)
+        px_rot_fft, py_rot_fft = oper.gradfft_from_fft(rot_fft)
+        px_b_fft, py_b_fft = oper.gradfft_from_fft(b_fft)
+        px_rot, py_rot, px_b, py_b = self.fields_tmp[2:6]
+        oper.ifft_as_arg(px_rot_fft, px_rot)
+        oper.ifft_as_arg(py_rot_fft, py_rot)
+        oper.ifft_as_arg(px_b_fft, px_b)
+        oper.ifft_as_arg(py_b_fft, py_b)
+        if self.solver == "ns2d.strat":
+            f_rot = -ux * px_rot - uy * py_rot
+            f_b = -ux * px_b - uy * py_b - self.N**2 * uy
+        else:
+            f_rot = -ux * px_rot - uy * py_rot + px_b
+            f_b = -ux * px_b - uy * py_b
+        oper.fft_as_arg(f_b, f_b_fft)
+        oper.fft_as_arg(f_rot, f_rot_fft)
+        if self.solver == "ns2d.strat":
+            f_rot_fft += px_b_fft  # strat/solver.py:156
+        self.dealiasing(tendencies_fft)
+        if self.forcing_fft is not None:
             tendencies_fft += self.forcing_fft
         return tendencies_fft
 
@@ -540,7 +594,10 @@ class OracleSim:
             ux = velo_max * ux / vmax
             uy = velo_max * uy / vmax
             rot_fft = oper.rotfft_from_vecfft(oper.fft(ux), oper.fft(uy))
-            self.set_state_spect(rot_fft[None])
+            if self.solver == "ns2d":
+                self.set_state_spect(rot_fft[None])
+            else:  # init_from_rotfft: b = 0 (ns2d/strat/state.py:233-236, ns2d/bouss/state.py:140-142)
+                self.set_state_spect(np.stack([rot_fft, np.zeros_like(rot_fft)]))
 
     def init_taylor_green(self):
         """doc/test_cases/Taylor_Green_vortices/run_simul.py:40-54."""

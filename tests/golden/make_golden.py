@@ -57,6 +57,12 @@ CASES = {
     # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
     "ns3d_16x16x16_rk4_forced": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=2e-2)),
     "strat_16x16x16_rk4_forced": ("ns3d.strat", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=2e-2, N=2.0)),
+    # f-4 breadth: ns2d.strat / ns2d.bouss (solvers/ns2d/strat/solver.py:71-181, bouss/solver.py:65-173);
+    # the b field of the initial state is a second noise realisation (the noise recipe leaves b = 0)
+    "ns2d_strat_32x32_rk4": ("ns2d.strat", (32, 32), 5, dict(nu_8=1e-8, deltat0=1e-2, N=1.5, Lx=8.0, Ly=8.0)),
+    "ns2d_strat_32x16_rk2": ("ns2d.strat", (32, 16), 4, dict(nu_2=1e-3, deltat0=1e-2, N=0.7, type_time_scheme="RK2", Lx=8.0, Ly=5.0)),
+    "ns2d_strat_24x15_rk4_odd": ("ns2d.strat", (24, 15), 3, dict(nu_2=1e-3, deltat0=2e-2, N=1.0, Lx=8.0, Ly=8.0)),
+    "ns2d_bouss_32x32_rk4": ("ns2d.bouss", (32, 32), 5, dict(nu_4=1e-5, deltat0=1e-2, Lx=8.0, Ly=8.0)),
     "ns2d_32x32_rk4_forced": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=2e-2, Lx=8.0, Ly=8.0)),
 }
 
@@ -108,6 +114,10 @@ def main():
         o = step_np.OracleSim(solver, nx, ny, nz, **okw)
         o.init_noise()
         s0 = np.array(o.state_spect)
+        if solver in ("ns2d.strat", "ns2d.bouss"):
+            o2 = step_np.OracleSim(solver, nx, ny, nz, **okw)
+            o2.init_noise(seed=7)
+            s0[1] = 0.5 * np.array(o2.state_spect)[0]
         params = refshim.make_params(solver, nx, ny, nz, **kw)
         if random_seed is not None:
             import random

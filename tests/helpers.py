@@ -67,7 +67,7 @@ def make_gpu_sim(meta, fused=None, mask=None):
     for key in ("Lx", "Ly", "Lz", "coef_dealiasing", "truncation_shape"):
         if key in kw:
             setattr(p.oper, key, kw.pop(key))
-    if solver != "ns2d":
+    if not solver.startswith("ns2d"):
         p.oper.Lx = meta["params"].get("Lx", 2 * np.pi)
         p.oper.Ly = meta["params"].get("Ly", 2 * np.pi)
         p.oper.Lz = meta["params"].get("Lz", 2 * np.pi)
