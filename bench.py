@@ -86,6 +86,42 @@ def host_mem_available():
     return 0
 
 
+def e2e_pipelined(S, host_in, ts, sim, slab, nb, barrier):
+    """Seconds per batch of `nb` independent batches streamed host -> device -> step -> host."""
+    import torch
+
+    host_out = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+    S_in, S_out = torch.empty_like(S), torch.empty_like(S)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(nb + 2):
+        if i < nb:  # H2D of batch i
+            with torch.cuda.stream(s_in):
+                S_in.copy_(host_in, non_blocking=True)
+        if 1 <= i <= nb:  # step of batch i-1 (S was loaded from S_in at the end of the previous round)
+            if slab:
+                sim.mark_spect_modified()
+            else:
+                sim.state.mark_spect_modified()
+            ts.one_time_step()
+        if i >= 2:  # D2H of the result of batch i-2
+            with torch.cuda.stream(s_out):
+                host_out.copy_(S_out, non_blocking=True)
+        torch.cuda.synchronize()
+        if 1 <= i <= nb:
+            S_out.copy_(S)
+        if i < nb:
+            S.copy_(S_in)
+    torch.cuda.synchronize()
+    barrier()
+    dt = (time.perf_counter() - t0) / nb
+    del host_out, S_in, S_out
+    torch.cuda.empty_cache()
+    return dt
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -569,8 +605,38 @@ def own_arm(args):
             dt = float(tt.item())
         nbytes = S.numel() * 16 * world
         e2e = {"value": npts / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "steps": ksteps,
+               "ms_per_step": dt * 1e3, "steps": ksteps, "mode": "serial",
                "note": "whole-job bytes (all ranks); each rank copies its slab over its own PCIe link"}
+        # The same work as a 3-stage pipeline over independent batches (a "step" = one pass of the hot
+        # path over one batch): H2D of batch k+1 and D2H of the result of batch k-1 run on their own
+        # streams (two copy engines, PCIe full duplex) under the step of batch k.  Needs two more state
+        # buffers on the device; every rank takes the same decision.
+        pipe = None
+        try:
+            torch.cuda.empty_cache()
+            free_dev, _ = torch.cuda.mem_get_info()
+            ok = free_dev > 2 * S.numel() * 16 + (6 << 30) and host_mem_available() > 2 * S.numel() * 16
+            if world > 1:
+                okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+                ok = bool(okt.item() > 0.5)
+            if ok:
+                pipe = e2e_pipelined(S, host, ts, sim, slab, max(6, min(args.steps, 10)), barrier)
+                if world > 1:
+                    tt = torch.tensor([pipe], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    pipe = float(tt.item())
+        except Exception as exc:  # the serial figure above stands
+            e2e["pipelined_note"] = f"pipelined run failed: {type(exc).__name__}: {str(exc)[:120]}"
+            pipe = None
+        if pipe is not None and 0 < pipe < dt:
+            e2e.update({"value": npts / pipe, "ms_per_step": pipe * 1e3, "mode": "pipelined",
+                        "serial_ms_per_step": dt * 1e3, "serial_value": npts / dt,
+                        "note": e2e["note"] + "; pipelined over independent batches: the H2D copy of batch "
+                                "k+1 and the D2H copy of the result of batch k-1 overlap the step of batch k "
+                                "(time = fill + batches + drain, divided by the number of batches)"})
+        elif pipe is not None:
+            e2e["pipelined_ms_per_step"] = pipe * 1e3
         del host
 
     cpu_baseline = None
