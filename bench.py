@@ -621,7 +621,8 @@ def own_arm(args):
                 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
                 ok = bool(okt.item() > 0.5)
             if ok:
-                pipe = e2e_pipelined(S, host, ts, sim, slab, max(6, min(args.steps, 10)), barrier)
+                nbatch = max(6, min(args.steps, 10))
+                pipe = e2e_pipelined(S, host, ts, sim, slab, nbatch, barrier)
                 if world > 1:
                     tt = torch.tensor([pipe], dtype=torch.float64, device="cuda")
                     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -630,8 +631,8 @@ def own_arm(args):
             e2e["pipelined_note"] = f"pipelined run failed: {type(exc).__name__}: {str(exc)[:120]}"
             pipe = None
         if pipe is not None and 0 < pipe < dt:
-            e2e.update({"value": npts / pipe, "ms_per_step": pipe * 1e3, "mode": "pipelined",
-                        "serial_ms_per_step": dt * 1e3, "serial_value": npts / dt,
+            e2e.update({"value": npts / pipe, "ms_per_step": pipe * 1e3, "mode": "pipelined", "steps": nbatch,
+                        "serial_ms_per_step": dt * 1e3, "serial_value": npts / dt, "serial_steps": ksteps,
                         "note": e2e["note"] + "; pipelined over independent batches: the H2D copy of batch "
                                 "k+1 and the D2H copy of the result of batch k-1 overlap the step of batch k "
                                 "(time = fill + batches + drain, divided by the number of batches)"})

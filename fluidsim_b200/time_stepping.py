@@ -403,23 +403,37 @@ class TimeSteppingPseudoSpectralB200:
         diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
         S = self.sim.state.state_spect.tensor
         alpha, beta = self._get_phaseshift_random()
-        tendencies_0 = self._shifted_tendencies(alpha, S)
+        # both evaluations write their result over their input in the reference (:687-702)
+        tendencies_0 = self._shifted_tendencies_aliased(alpha, S) / alpha
         state_spect_1 = self._rk2_first_half(tendencies_0, diss)
-        tendencies_1 = self._shifted_tendencies(beta, state_spect_1.tensor)
+        tendencies_1 = self._shifted_tendencies_aliased(beta, state_spect_1.tensor) / beta
         tendencies_d = 0.5 * (tendencies_0 + tendencies_1)
         self._step_like_rk2(tendencies_d, diss, diss2)
+
+    def _shifted_tendencies_aliased(self, phaseshift, state_tensor):
+        """The reference evaluates ``compute_tendencies(state_spect_shift, old=state_spect_shift)``
+        (pseudo_spect.py:764-766, 777-779): the output array IS the input array.  For ns3d.strat this
+        changes the reference's result -- ``fb_fft`` is formed from ``vz_fft`` after ``fz_fft + b_fft``
+        was written over it (strat/solver.py:198-207) -- so that solver evaluates the aliased call through
+        the same operator-level sequence to stay identical to the reference; the other solvers read
+        everything they need before the first write and may use the fused kernels."""
+        sim = self.sim
+        shifted = self._like_state(phaseshift * state_tensor)
+        if sim.short_name == "ns3d.strat":
+            return sim.tendencies_nonlin(shifted, old=shifted).tensor
+        return self._compute_tendencies(shifted).tensor
 
     def _time_step_RK2_phaseshift_exact(self):
         """pseudo_spect.py:735-796."""
         diss, diss2 = self.exact_linear_coefs.get_updated_coefs()
         S = self.sim.state.state_spect.tensor
         phaseshift = self._get_phaseshift()
-        tendencies_0 = self._compute_tendencies().tensor.clone()
-        tendencies_0_shift = self._compute_tendencies(self._like_state(phaseshift * S)).tensor
+        tendencies_0 = self._compute_tendencies(self._like_state(S)).tensor
+        tendencies_0_shift = self._shifted_tendencies_aliased(phaseshift, S)
         tendencies_d0 = 0.5 * (tendencies_0 + tendencies_0_shift / phaseshift)
         state_spect_1 = self._rk2_first_half(tendencies_d0, diss)
-        tendencies_1 = self._compute_tendencies(state_spect_1).tensor.clone()
-        tendencies_1_shift = self._compute_tendencies(self._like_state(phaseshift * state_spect_1.tensor)).tensor
+        tendencies_1 = self._compute_tendencies(state_spect_1).tensor
+        tendencies_1_shift = self._shifted_tendencies_aliased(phaseshift, state_spect_1.tensor)
         tendencies_d = 0.5 * (tendencies_d0 + 0.5 * (tendencies_1 + tendencies_1_shift / phaseshift))
         self._step_like_rk2(tendencies_d, diss, diss2)
 

@@ -52,6 +52,7 @@ CASES = {
     "strat_16x16x16_rk2_phaseshift_exact": ("ns3d.strat", (16, 16, 16), 3, dict(nu_2=1e-2, deltat0=1e-2, N=2.0, type_time_scheme="RK2_phaseshift_exact")),
     "ns2d_32x32_rk2_phaseshift": ("ns2d", (32, 32), 4, dict(nu_8=1e-8, deltat0=1e-2, Lx=8.0, Ly=8.0, type_time_scheme="RK2_phaseshift")),
     "ns3d_16x16x16_rk2_phaseshift_random": ("ns3d", (16, 16, 16), 5, dict(nu_2=1e-2, deltat0=1e-2, type_time_scheme="RK2_phaseshift_random", random_seed=11)),
+    "strat_16x16x16_rk2_phaseshift_random": ("ns3d.strat", (16, 16, 16), 4, dict(nu_2=1e-2, deltat0=1e-2, N=2.0, type_time_scheme="RK2_phaseshift_random", random_seed=3)),
     "ns2d_32x32_euler_phaseshift_random": ("ns2d", (32, 32), 5, dict(nu_8=1e-8, deltat0=5e-3, Lx=8.0, Ly=8.0, type_time_scheme="Euler_phaseshift_random", random_seed=5)),
     # forced cases: a constant forcing_fft on the shell 2 <= |k|/dk <= 3.5 handed to the reference's
     # tendencies_nonlin through a stub `sim.forcing` (get_forcing()), forcing.enable = True
