@@ -133,7 +133,8 @@ class _Writer:
         msgs = [
             _message(0x0001, _dataspace_message(arr.shape)),
             _message(0x0003, _datatype_message(arr.dtype), flags=1),
-            _message(0x0005, struct.pack("<BBBB", 2, 2, 2, 0)),  # fill value v2: late alloc, undefined
+            # fill value v2: late allocation, written "if set", default fill value (defined, size 0)
+            _message(0x0005, struct.pack("<BBBBI", 2, 2, 2, 1, 0)),
             _message(0x0008, struct.pack("<BBQQ", 3, 1, data_addr, len(raw))),  # contiguous layout v3
         ]
         return self.alloc(_object_header(msgs))

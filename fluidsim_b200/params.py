@@ -120,4 +120,6 @@ def create_default_params(solver="ns3d"):
     p.forcing._set_child("tcrandom", dict(time_correlation="based_on_forcing_rate"))
     p._set_child("init_fields", dict(type="constant"))
     p.init_fields._set_child("noise", dict(velo_max=1.0, length=None))
+    p.init_fields._set_child("from_file", dict(path=""))  # base/init_fields.py:144-151
+    p._set_child("output", dict(path_run=None))
     return p

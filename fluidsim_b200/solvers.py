@@ -19,6 +19,29 @@ from .state import StateNS2D, StateNS2DStrat, StateNS3D, StateNS3DStrat
 from .time_stepping import TimeSteppingPseudoSpectralB200
 
 
+class PhysFieldsB200:
+    """``sim.output.phys_fields.save()`` (base/output/phys_fields.py:130-202)."""
+
+    def __init__(self, output):
+        self.output = output
+
+    def save(self, state_phys=None, params=None, particular_attr=None):
+        from .checkpoint import save_state_phys
+
+        out = self.output
+        return save_state_phys(out.sim, out.path_run, out.name_run, particular_attr=particular_attr)
+
+
+class OutputB200:
+    """The slice of ``OutputBase`` the checkpoint needs: ``path_run``, ``name_run``, ``phys_fields``."""
+
+    def __init__(self, sim):
+        self.sim = sim
+        self.name_run = f"{sim.short_name}_b200"
+        self.path_run = getattr(getattr(sim.params, "output", None), "path_run", None) or "."
+        self.phys_fields = PhysFieldsB200(self)
+
+
 class SimulBasePseudoSpectralB200:
     short_name = None
     ndim = 3
@@ -51,6 +74,15 @@ class SimulBasePseudoSpectralB200:
             from .forcing import ForcingB200
 
             self.forcing = ForcingB200(self)
+        # base/solvers/base.py:196-216: output object, then the initial fields.  Only the checkpoint
+        # pieces of both exist here: output.phys_fields.save() and
+        # init_fields.type = "from_file"; other initial conditions are set through the state container.
+        self.output = OutputB200(self)
+        init = getattr(params, "init_fields", None)
+        if init is not None and getattr(init, "type", None) == "from_file":
+            from .checkpoint import load_state_phys
+
+            load_state_phys(self, init.from_file.path)
 
     def _init_projection(self):
         pass
