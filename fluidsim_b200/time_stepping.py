@@ -328,9 +328,12 @@ class TimeSteppingPseudoSpectralB200:
             self._previous_index_flip = index_flip
             alpha, beta = pair if index_flip else pair[::-1]
         if self._index_phaseshift == nb_steps:
+            # the reference re-binds (alpha, beta) to the arrays of the oldest pair and overwrites them
+            # in place with the new phases (:362-369): this step already uses the NEW pair
             self._index_phaseshift = 1
             self._pairs_phaseshift.pop(0)
-            self._pairs_phaseshift.append(self._new_random_pair())
+            alpha, beta = self._new_random_pair()
+            self._pairs_phaseshift.append((alpha, beta))
         else:
             self._index_phaseshift += 1
         return alpha, beta

@@ -242,7 +242,10 @@ def make_params(solver, nx, ny, nz=None, Lx=2 * np.pi, Ly=2 * np.pi, Lz=2 * np.p
         ),
     )
     # TimeSteppingPseudoSpectral._complete_params_with_default (pseudo_spect.py:159-167)
-    p.time_stepping._set_child("phaseshift_random", dict(nb_pairs=1, nb_steps_compute_new_pair=None))
+    p.time_stepping._set_child(
+        "phaseshift_random",
+        dict(nb_pairs=kw.pop("nb_pairs", 1), nb_steps_compute_new_pair=kw.pop("nb_steps_compute_new_pair", None)),
+    )
     p._set_child("forcing", dict(enable=False))
     if solver.startswith("ns3d"):
         p.f = kw.pop("f", None)

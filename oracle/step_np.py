@@ -97,8 +97,14 @@ class OracleSim:
         beta=0.0,
         no_vz_kz0=False,
         projection=None,
+        nb_pairs=1,
+        nb_steps_compute_new_pair=None,
     ):
         self.solver = solver
+        # params.time_stepping.phaseshift_random (pseudo_spect.py:159-167)
+        self.nb_pairs = nb_pairs
+        self.nb_steps_compute_new_pair = nb_steps_compute_new_pair
+        self._phaseshift = None
         self.nu_2, self.nu_4, self.nu_8, self.nu_m4 = nu_2, nu_4, nu_8, nu_m4
         self.N, self.f, self.beta = N, f, beta
         self.no_vz_kz0 = bool(no_vz_kz0)
@@ -152,6 +158,8 @@ class OracleSim:
         self.exact2 = np.exp(-self.deltat / 2 * self.freq_lin)
         self._state_spect_tmp = np.empty_like(self.state_spect)
         self._state_spect_tmp1 = np.empty_like(self.state_spect)
+        if type_time_scheme.endswith("_random"):  # pseudo_spect.py:210-216
+            self._init_phaseshift_random()
 
     # ------------------------------------------------------------------ linear term
     def compute_freq_diss(self):
@@ -432,14 +440,184 @@ class OracleSim:
         tendencies_3 = self.tendencies_nonlin(state_spect_1_approx, old=tendencies_2)
         state_spect[:] = state_spect_tmp + dt / 6 * tendencies_3  # :984
 
+    # ---- Euler / trapezoid / phase-shifting schemes (pseudo_spect.py:245-468, 519-796)
+    def _get_phaseshift(self):
+        """pseudo_spect.py:281-300."""
+        if self._phaseshift is None:
+            oper = self.oper
+            if self.ndim == 2:
+                phase = 0.5 * (oper.deltax * oper.KX + oper.deltay * oper.KY)
+            else:
+                phase = 0.5 * (oper.deltax * oper.Kx + oper.deltay * oper.Ky + oper.deltaz * oper.Kz)
+            self._phaseshift = np.exp(1j * phase)
+        return self._phaseshift
+
+    def _get_phases_random(self):
+        """operators3d.py:1128-1146 / operators2d.py:618-631 (Python's `random`, not numpy's)."""
+        from random import uniform
+
+        oper = self.oper
+        if self.ndim == 3:
+            alpha_x, alpha_y, alpha_z = tuple(uniform(-0.5, 0.5) for _ in range(3))
+            beta_x = alpha_x + 0.5 if alpha_x < 0 else alpha_x - 0.5
+            beta_y = alpha_y + 0.5 if alpha_y < 0 else alpha_y - 0.5
+            beta_z = alpha_z + 0.5 if alpha_z < 0 else alpha_z - 0.5
+            phase_alpha = (
+                alpha_x * oper.deltax * oper.Kx + alpha_y * oper.deltay * oper.Ky + alpha_z * oper.deltaz * oper.Kz
+            )
+            phase_beta = beta_x * oper.deltax * oper.Kx + beta_y * oper.deltay * oper.Ky + beta_z * oper.deltaz * oper.Kz
+        else:
+            alpha_x, alpha_y = tuple(uniform(-0.5, 0.5) for _ in range(2))
+            beta_x = alpha_x + 0.5 if alpha_x < 0 else alpha_x - 0.5
+            beta_y = alpha_y + 0.5 if alpha_y < 0 else alpha_y - 0.5
+            phase_alpha = alpha_x * oper.deltax * oper.KX + alpha_y * oper.deltay * oper.KY
+            phase_beta = beta_x * oper.deltax * oper.KX + beta_y * oper.deltay * oper.KY
+        return phase_alpha, phase_beta
+
+    def _init_phaseshift_random(self):
+        """pseudo_spect.py:302-328."""
+        if self.nb_steps_compute_new_pair is None:
+            self.nb_steps_compute_new_pair = 2 if self.nb_pairs == 1 else 4 * self.nb_pairs
+        self._index_phaseshift = 1
+        self._previous_index_pair = 0
+        self._previous_index_flip = 0
+        self._pairs_phaseshift = []
+        for _ in range(self.nb_pairs):
+            phase_alpha, phase_beta = self._get_phases_random()
+            self._pairs_phaseshift.append((np.exp(1j * phase_alpha), np.exp(1j * phase_beta)))
+
+    def _get_phaseshift_random(self):
+        """pseudo_spect.py:330-372.  On the step that renews the oldest pair the reference re-binds
+        (alpha, beta) to that pair's arrays and overwrites them in place (compute_phaseshift_terms,
+        :91-100): the step then uses the NEW pair, in (alpha, beta) order."""
+        from random import randint
+
+        nb_pairs, nb_steps = self.nb_pairs, self.nb_steps_compute_new_pair
+        if nb_pairs == 1 and nb_steps == 1:
+            phaseshift_alpha, phaseshift_beta = self._pairs_phaseshift[0]
+        elif nb_pairs == 1 and nb_steps == 2:
+            pair = self._pairs_phaseshift[0]
+            if self._index_phaseshift == 1:
+                phaseshift_alpha, phaseshift_beta = pair
+            else:
+                phaseshift_beta, phaseshift_alpha = pair
+        else:
+            index_pair = randint(0, nb_pairs - 1)
+            pair = self._pairs_phaseshift[index_pair]
+            index_flip = randint(0, 1)
+            if index_pair == self._previous_index_pair and index_flip == self._previous_index_flip:
+                index_flip = 0 if index_flip else 1
+            self._previous_index_pair = index_pair
+            self._previous_index_flip = index_flip
+            if index_flip:
+                phaseshift_alpha, phaseshift_beta = pair
+            else:
+                phaseshift_beta, phaseshift_alpha = pair
+        if self._index_phaseshift == nb_steps:
+            self._index_phaseshift = 1
+            phase_alpha, phase_beta = self._get_phases_random()
+            phaseshift_alpha, phaseshift_beta = self._pairs_phaseshift.pop(0)
+            phaseshift_alpha[:] = np.exp(1j * phase_alpha)
+            phaseshift_beta[:] = np.exp(1j * phase_beta)
+            self._pairs_phaseshift.append((phaseshift_alpha, phaseshift_beta))
+        else:
+            self._index_phaseshift += 1
+        return phaseshift_alpha, phaseshift_beta
+
+    def _like_state(self, arr):
+        out = SetOfVariables(like=self.state_spect)
+        out[...] = arr
+        return out
+
+    def _time_step_Euler(self):
+        """pseudo_spect.py:245-279."""
+        tendencies_0 = self.tendencies_nonlin()
+        self.state_spect[:] = (self.state_spect + self.deltat * tendencies_0) * self.exact
+
+    def _time_step_Euler_phaseshift(self):
+        """pseudo_spect.py:374-420."""
+        state_spect = self.state_spect
+        tendencies_0 = self.tendencies_nonlin()
+        phaseshift = self._get_phaseshift()
+        tendencies_shifted = self.tendencies_nonlin(self._like_state(phaseshift * state_spect)) / phaseshift
+        tendencies_dealiased = 0.5 * (tendencies_0 + tendencies_shifted)
+        state_spect[:] = (state_spect + self.deltat * tendencies_dealiased) * self.exact
+
+    def _time_step_Euler_phaseshift_random(self):
+        """pseudo_spect.py:422-467."""
+        state_spect = self.state_spect
+        phaseshift_alpha, phaseshift_beta = self._get_phaseshift_random()
+        tendencies_alpha = self.tendencies_nonlin(self._like_state(phaseshift_alpha * state_spect)) / phaseshift_alpha
+        tendencies_beta = self.tendencies_nonlin(self._like_state(phaseshift_beta * state_spect)) / phaseshift_beta
+        tendencies_dealiased = 0.5 * (tendencies_alpha + tendencies_beta)
+        state_spect[:] = (state_spect + self.deltat * tendencies_dealiased) * self.exact
+
+    def _time_step_RK2_trapezoid(self):
+        """pseudo_spect.py:519-569."""
+        dt = self.deltat
+        diss = self.exact
+        state_spect = self.state_spect
+        tendencies_0 = self.tendencies_nonlin()
+        state_spect_1 = step_Euler(state_spect, dt, tendencies_0, diss, output=self._state_spect_tmp)
+        tendencies_1 = self.tendencies_nonlin(state_spect_1)
+        state_spect[:] = (state_spect + dt / 2 * tendencies_0) * diss + dt / 2 * tendencies_1
+
+    def _time_step_RK2_phaseshift(self):
+        """pseudo_spect.py:571-638."""
+        dt = self.deltat
+        diss, diss2 = self.exact, self.exact2
+        state_spect = self.state_spect
+        tendencies_0 = self.tendencies_nonlin()
+        state_spect_1 = step_Euler(state_spect, dt, tendencies_0, diss, output=self._state_spect_tmp)
+        phaseshift = self._get_phaseshift()
+        tendencies_1_shift = self.tendencies_nonlin(self._like_state(phaseshift * state_spect_1))
+        tendencies_d = self._state_spect_tmp
+        tendencies_d[:] = 0.5 * (tendencies_0 + tendencies_1_shift / phaseshift)
+        step_like_RK2(state_spect, dt, tendencies_d, diss, diss2)
+
+    def _time_step_RK2_phaseshift_random(self):
+        """pseudo_spect.py:640-709.  Both tendencies calls write their result over their input
+        (``old=state_spect_shift``), which changes what ns3d.strat computes for fb_fft."""
+        dt = self.deltat
+        diss, diss2 = self.exact, self.exact2
+        phaseshift_alpha, phaseshift_beta = self._get_phaseshift_random()
+        state_spect = self.state_spect
+        state_spect_shift = self._like_state(phaseshift_alpha * state_spect)
+        tendencies_0_shift = self.tendencies_nonlin(state_spect_shift, old=state_spect_shift)
+        tendencies_0_shift /= phaseshift_alpha  # div_inplace
+        tendencies_0 = tendencies_0_shift
+        state_spect_1 = step_Euler(state_spect, dt, tendencies_0, diss, output=self._state_spect_tmp)
+        state_spect_1_shift = self._like_state(phaseshift_beta * state_spect_1)
+        tendencies_1_shift = self.tendencies_nonlin(state_spect_1_shift, old=state_spect_1_shift)
+        tendencies_d = self._state_spect_tmp
+        tendencies_d[:] = 0.5 * (tendencies_0 + tendencies_1_shift / phaseshift_beta)  # mean_with_phaseshift
+        step_like_RK2(state_spect, dt, tendencies_d, diss, diss2)
+
+    def _time_step_RK2_phaseshift_exact(self):
+        """pseudo_spect.py:711-796 (the two shifted evaluations alias output and input, see above)."""
+        dt = self.deltat
+        diss, diss2 = self.exact, self.exact2
+        phaseshift = self._get_phaseshift()
+        state_spect = self.state_spect
+        tmp0 = SetOfVariables(like=state_spect)
+        tendencies_0 = self.tendencies_nonlin(state_spect, old=tmp0)
+        state_spect_shift = self._like_state(phaseshift * state_spect)
+        tendencies_0_shift = self.tendencies_nonlin(state_spect_shift, old=state_spect_shift)
+        tendencies_d0 = 0.5 * (tendencies_0 + tendencies_0_shift / phaseshift)
+        state_spect_1 = step_Euler(state_spect, dt, tendencies_d0, diss, output=self._state_spect_tmp)
+        tendencies_1 = self.tendencies_nonlin(state_spect_1, old=tmp0)
+        state_spect_shift = self._like_state(phaseshift * state_spect_1)
+        tendencies_1_shift = self.tendencies_nonlin(state_spect_shift, old=state_spect_shift)
+        tendencies_d = 0.5 * (tendencies_d0 + 0.5 * (tendencies_1 + tendencies_1_shift / phaseshift))
+        step_like_RK2(state_spect, dt, tendencies_d, diss, diss2)
+
     def one_time_step(self):
         """ns3d/time_stepping.py:8-20 (3-D) / pseudo_spect.py:236-243 (2-D) + base.py:243-244."""
-        if self.scheme == "RK4":
-            self._time_step_RK4()
-        elif self.scheme == "RK2":
-            self._time_step_RK2()
-        else:
+        schemes = ("RK4", "RK2", "Euler", "Euler_phaseshift", "Euler_phaseshift_random", "RK2_trapezoid",
+                   "RK2_phaseshift", "RK2_phaseshift_random", "RK2_phaseshift_exact")
+        if self.scheme not in schemes:  # pseudo_spect.py:191-224
             raise ValueError(f'Problem name time_scheme ("{self.scheme}")')
+        getattr(self, "_time_step_" + self.scheme)()
         if self.ndim == 3:
             self.project_state_spect(self.state_spect)
         self.dealiasing(self.state_spect)

@@ -33,19 +33,23 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-ORACLE_SCHEMES = ("RK2", "RK4")
-
-
-def make_oracle(meta):
-    """Numpy oracle for a golden / test case.  The oracle restates RK2 and RK4 only; for goldens of
-    the other schemes (made by the reference's own time stepper) it still provides operators,
-    tendencies and observables, built with RK4."""
+def make_oracle(meta, stepping=False):
+    """Numpy oracle for a golden / test case.  By default it only provides operators, tendencies and
+    observables (built with RK4 when the case uses a *_random scheme, so that constructing it draws
+    nothing from Python's `random`).  ``stepping=True``: the oracle of the case's own scheme, with the
+    recorded ``random_seed`` applied right before construction, like the reference run that made the
+    golden."""
     from oracle import step_np
 
     shape = meta["shape"]
     nz = shape[2] if len(shape) == 3 else None
     kw = dict(meta["params"])
-    if kw.get("type_time_scheme", "RK4") not in ORACLE_SCHEMES:
+    if stepping:
+        if "random_seed" in meta:
+            import random
+
+            random.seed(meta["random_seed"])
+    elif kw.get("type_time_scheme", "RK4").endswith("_random"):
         kw["type_time_scheme"] = "RK4"
     return step_np.OracleSim(meta["solver"], shape[0], shape[1], nz, **kw)
 
@@ -77,6 +81,9 @@ def make_gpu_sim(meta, fused=None, mask=None):
     p.time_stepping.USE_CFL = False
     p.time_stepping.type_time_scheme = kw.pop("type_time_scheme", "RK4")
     p.time_stepping.deltat0 = kw.pop("deltat0", 1e-2)
+    for key in ("nb_pairs", "nb_steps_compute_new_pair"):  # pseudo_spect.py:159-167
+        if key in kw:
+            setattr(p.time_stepping.phaseshift_random, key, kw.pop(key))
     for key in ("nu_2", "nu_4", "nu_8", "nu_m4", "f", "N", "beta", "no_vz_kz0", "projection"):
         if key in kw:
             setattr(p, key, kw.pop(key))

@@ -10,15 +10,13 @@ from oracle import refshim, step_np
 @pytest.mark.parametrize("name", all_golden_cases())
 def test_oracle_matches_golden(name):
     meta, z = load_golden(name)
-    o = make_oracle(meta)
+    o = make_oracle(meta, stepping=True)  # every scheme of the reference's stepper is restated
     assert np.array_equal(o.oper.where_dealiased, z["mask"])
     o.set_state_spect(z["state0"])
     if "forcing" in z.files:  # forced goldens: tendencies += forcing_fft (solvers/ns3d/solver.py:243-244)
         o.forcing_fft = z["forcing"]
     tend = np.array(o.tendencies_nonlin())
     assert rel_err(tend, z["tend0"]) < 1e-13
-    if meta["params"].get("type_time_scheme", "RK4") not in ("RK2", "RK4"):
-        return  # Euler / trapezoid / phase-shift goldens come straight from the reference's stepper
     o.one_time_step()
     assert rel_err(o.state_spect, z["state1"]) < 1e-13
     for _ in range(meta["nsteps"] - 1):
@@ -96,6 +94,49 @@ def test_oracle_equals_reference_code(solver, shape, kw):
         a = ref.step()
         b = np.array(o.one_time_step())
         assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize(
+    "solver,shape,kw",
+    [
+        ("ns3d", (16, 12, 8), dict(type_time_scheme="Euler")),
+        ("ns3d.strat", (16, 12, 8), dict(type_time_scheme="Euler_phaseshift", N=2.0)),
+        ("ns2d", (32, 24), dict(type_time_scheme="Euler_phaseshift_random", Lx=8, Ly=8)),
+        ("ns2d.strat", (16, 16), dict(type_time_scheme="Euler_phaseshift_random", nb_pairs=2, nb_steps_compute_new_pair=3, Lx=8, Ly=8)),
+        ("ns3d", (16, 12, 8), dict(type_time_scheme="RK2_trapezoid")),
+        ("ns3d.bouss", (16, 12, 8), dict(type_time_scheme="RK2_phaseshift")),
+        ("ns2d", (32, 24), dict(type_time_scheme="RK2_phaseshift", beta=0.2, Lx=8, Ly=8)),
+        ("ns3d", (16, 12, 8), dict(type_time_scheme="RK2_phaseshift_random")),
+        ("ns3d.strat", (16, 12, 8), dict(type_time_scheme="RK2_phaseshift_random", N=2.0, nb_pairs=3, nb_steps_compute_new_pair=2)),
+        ("ns3d.strat", (16, 12, 8), dict(type_time_scheme="RK2_phaseshift_exact", N=2.0)),
+        ("ns2d.strat", (16, 16), dict(type_time_scheme="RK2_phaseshift_exact", N=1.5, Lx=8, Ly=8)),
+    ],
+)
+def test_oracle_schemes_equal_reference_code(solver, shape, kw):
+    """Euler / trapezoid / phase-shift schemes (pseudo_spect.py:245-796), weakly dealiased
+    (coef_dealiasing = 0.9) so that the phase shifts -- and, for the random ones, the exact sequence of
+    draws and pair renewals -- change the result; six steps, bit for bit."""
+    import random
+
+    nx, ny = shape[0], shape[1]
+    nz = shape[2] if len(shape) == 3 else None
+    kw = dict(nu_2=1e-2, deltat0=1e-2, coef_dealiasing=0.9, **kw)
+    init = step_np.OracleSim(solver, nx, ny, nz, **{k: v for k, v in kw.items() if k != "type_time_scheme"})
+    init.init_noise()
+    s0 = np.array(init.state_spect)
+    if solver in ("ns2d.strat", "ns2d.bouss"):
+        s0 = with_buoyancy_2d(init, solver, nx, ny, {k: v for k, v in kw.items() if k != "type_time_scheme"})
+    random.seed(12)  # both implementations draw from Python's `random`: run them one after the other
+    ref = refshim.RefSim(solver, refshim.make_params(solver, nx, ny, nz, **kw))
+    ref.set_state_spect(s0)
+    ref_states = [ref.step() for _ in range(6)]
+    random.seed(12)
+    o = step_np.OracleSim(solver, nx, ny, nz, **kw)
+    o.set_state_spect(s0)
+    for a in ref_states:
+        assert np.array_equal(a, np.array(o.one_time_step()))
+    assert not np.array_equal(ref_states[0], s0)
 
 
 def test_spectrum3d_sums_to_energy():
