@@ -692,6 +692,9 @@ def own_arm(args):
                 "size_note": size_note,
                 "state_bytes_per_gpu": S.numel() * 16,
                 "l2_policy": "inputs larger than L2 (no flush needed)" if S.numel() * 16 > 200e6 else "L2-resident problem",
+                "note": "timed step = full RK4 step incl. end-of-step projection + dealiasing; state_phys is lazy "
+                        "on this path (the reference, and the CPU arm, refresh it with 3-4 inverse FFTs every "
+                        "step) and the per-step NaN check is done once after the timed region",
                 "parallelism": ("single GPU" if not force_slab else "slab code path on ONE rank (diagnostic)") if world == 1 else f"slab x{world} (z-slabs in X, ky-slabs in K; NCCL all-to-all; lean buffers)",
             },
             "nvlink": nvlink,
