@@ -615,7 +615,9 @@ def own_arm(args):
         try:
             torch.cuda.empty_cache()
             free_dev, _ = torch.cuda.mem_get_info()
-            ok = free_dev > 2 * S.numel() * 16 + (6 << 30) and host_mem_available() > 2 * S.numel() * 16
+            # single-GPU runs only: the multi-rank variant has not been exercised on a multi-GPU box
+            ok = (world == 1 and free_dev > 2 * S.numel() * 16 + (6 << 30)
+                  and host_mem_available() > 2 * S.numel() * 16)
             if world > 1:
                 okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
                 dist.all_reduce(okt, op=dist.ReduceOp.MIN)
