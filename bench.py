@@ -610,7 +610,7 @@ def own_arm(args):
         # The same work as a 3-stage pipeline over independent batches (a "step" = one pass of the hot
         # path over one batch): H2D of batch k+1 and D2H of the result of batch k-1 run on their own
         # streams (two copy engines, PCIe full duplex) under the step of batch k.  Needs two more state
-        # buffers on the device; every rank takes the same decision.
+        # buffers on the device.
         pipe = None
         try:
             torch.cuda.empty_cache()
@@ -618,17 +618,9 @@ def own_arm(args):
             # single-GPU runs only: the multi-rank variant has not been exercised on a multi-GPU box
             ok = (world == 1 and free_dev > 2 * S.numel() * 16 + (6 << 30)
                   and host_mem_available() > 2 * S.numel() * 16)
-            if world > 1:
-                okt = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
-                dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-                ok = bool(okt.item() > 0.5)
             if ok:
                 nbatch = max(6, min(args.steps, 10))
                 pipe = e2e_pipelined(S, host, ts, sim, slab, nbatch, barrier)
-                if world > 1:
-                    tt = torch.tensor([pipe], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                    pipe = float(tt.item())
         except Exception as exc:  # the serial figure above stands
             e2e["pipelined_note"] = f"pipelined run failed: {type(exc).__name__}: {str(exc)[:120]}"
             pipe = None
