@@ -99,6 +99,8 @@ def create_default_params(solver="ns3d"):
             max_elapsed=None,
         ),
     )
+    if solver == "ns2d.strat":  # ns2d/strat/time_stepping.py:24-29
+        p.time_stepping.cfl_coef_group = None
     # pseudo_spect.py:159-167
     p.time_stepping._set_child("phaseshift_random", dict(nb_pairs=1, nb_steps_compute_new_pair=None))
     # base/forcing/base.py:63-76, 189-196; specific.py:436-451, 777-786

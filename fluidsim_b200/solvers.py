@@ -16,7 +16,7 @@ from .operators import OperatorsPseudoSpectral2D, OperatorsPseudoSpectral3D, vec
 from .params import create_default_params
 from .setofvariables import SetOfVariables
 from .state import StateNS2D, StateNS2DStrat, StateNS3D, StateNS3DStrat
-from .time_stepping import TimeSteppingPseudoSpectralB200
+from .time_stepping import TimeSteppingPseudoSpectralB200, TimeSteppingPseudoSpectralStratB200
 
 
 class PhysFieldsB200:
@@ -357,6 +357,7 @@ class SimulNS2DStrat(SimulNS2D):
 
     short_name = "ns2d.strat"
     State = StateNS2DStrat
+    TimeStepping = TimeSteppingPseudoSpectralStratB200  # ns2d/strat/solver.py:53-56
     supports_fused = False
     _bouss = 0
 
@@ -415,6 +416,7 @@ class SimulNS2DBouss(SimulNS2DStrat):
     """solvers/ns2d/bouss/solver.py:60-173."""
 
     short_name = "ns2d.bouss"
+    TimeStepping = TimeSteppingPseudoSpectralB200  # bouss keeps the base stepper (bouss/solver.py:30-57)
     _bouss = 1
 
 

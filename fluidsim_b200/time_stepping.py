@@ -477,3 +477,48 @@ class TimeSteppingPseudoSpectralB200:
              stream_ptr())
         tendencies_3 = sim.tendencies_nonlin(state_spect_tmp1, old=tendencies_2)
         call("b2_rk4_step3", h, S, acc, ptr(tendencies_3.tensor), dt, nvar, stream_ptr())
+
+
+class TimeSteppingPseudoSpectralStratB200(TimeSteppingPseudoSpectralB200):
+    """``solvers/ns2d/strat/time_stepping.py:19-186``: the ns2d.strat time stepper adds the time-step
+    limits of the internal gravity waves to the advective CFL rule."""
+
+    def _init_compute_time_step(self):
+        super()._init_compute_time_step()
+        from math import pi
+
+        oper = self.sim.oper
+        N = float(self.params.N)
+        self.coef_deltat_dispersion_relation = 1.0
+        self.coef_group = getattr(self.params.time_stepping, "cfl_coef_group", 1.0)
+        self.coef_phase = 1.0
+        KX, KZ = oper.KX, oper.KY
+        K_not0 = torch.sqrt(oper.K2_not0)
+        # compute_dispersion_relation (ns2d/strat/solver.py:215-225)
+        freq_disp_relation = float((N * (KX / K_not0)).max().item())
+        self.deltat_dispersion_relation = self.coef_deltat_dispersion_relation * (2.0 * pi / freq_disp_relation)
+        if self.coef_group:  # _compute_time_increment_group_and_phase (:109-139)
+            cg_kx = (N / K_not0) * (KZ**2 / K_not0**2)
+            cg_kz = (-N / K_not0) * ((KX / K_not0) * (KZ / K_not0))
+            freq_group = float(cg_kx.max().item()) / oper.deltax + float(cg_kz.max().item()) / oper.deltay
+            freq_phase = float((N * (KX / K_not0**2)).max().item()) / oper.deltax
+            self.deltat_group_vel = self.coef_group / freq_group
+            self.deltat_phase_vel = self.coef_phase / freq_phase
+        if self.params.forcing.enable:  # _compute_time_increment_forcing (:100-107)
+            self.deltat_f = 1.0 / (self.params.forcing.forcing_rate ** (1.0 / 3))
+
+    def compute_time_increment_CLF(self):
+        """_compute_time_increment_CFL_uxuyb (:141-186)."""
+        get_var = self.sim.state.get_var
+        oper = self.sim.oper
+        freq_CFL = self._max_abs(get_var("ux")) / oper.deltax + self._max_abs(get_var("uy")) / oper.deltay
+        deltat_CFL = self.CFL / freq_CFL if freq_CFL > 0 else self.deltat_max
+        if not self.coef_group:
+            maybe_new_dt = min(deltat_CFL, self.deltat_dispersion_relation, self.deltat_max)
+        else:
+            maybe_new_dt = min(deltat_CFL, self.deltat_dispersion_relation, self.deltat_group_vel, self.deltat_max)
+        if self.params.forcing.enable:
+            maybe_new_dt = min(maybe_new_dt, self.deltat_f)
+        normalize_diff = abs(self.deltat - maybe_new_dt) / maybe_new_dt
+        if normalize_diff > 0.02:
+            self.deltat = maybe_new_dt

@@ -644,9 +644,39 @@ class OracleSim:
             freq = np.abs(ux).max() / oper.deltax + np.abs(uy).max() / oper.deltay
         deltat_CFL = cfl / freq if freq > 0 else deltat_max
         deltat_wanted = min(deltat_CFL, deltat_max)
+        if self.solver == "ns2d.strat":  # _compute_time_increment_CFL_uxuyb, ns2d/strat/time_stepping.py:149-186
+            lim = self.strat_time_increments()
+            if not self.cfl_coef_group:
+                deltat_wanted = min(deltat_CFL, lim["dispersion_relation"], deltat_max)
+            else:
+                deltat_wanted = min(deltat_CFL, lim["dispersion_relation"], lim["group_vel"], deltat_max)
+            if self.forcing_rate is not None:
+                deltat_wanted = min(deltat_wanted, 1.0 / (self.forcing_rate ** (1.0 / 3)))
         if abs(self.deltat - deltat_wanted) / deltat_wanted > 0.02:  # base.py:350-354
             self.set_deltat(deltat_wanted)
         return self.deltat
+
+    # ns2d.strat: params.time_stepping.cfl_coef_group (None by default) and params.forcing.forcing_rate
+    # when the forcing is enabled (ns2d/strat/time_stepping.py:24-29,100-107)
+    cfl_coef_group = None
+    forcing_rate = None
+
+    def strat_time_increments(self):
+        """Wave time-step limits of ns2d.strat (ns2d/strat/time_stepping.py:57-98,109-147;
+        compute_dispersion_relation: ns2d/strat/solver.py:215-225)."""
+        oper = self.oper
+        N = self.N
+        KX, KZ, K_not0 = oper.KX, oper.KY, oper.K_not0
+        out = {"dispersion_relation": 1.0 * (2.0 * pi / (N * (KX / K_not0)).max())}
+        if self.cfl_coef_group:
+            cg_kx = (N / K_not0) * (KZ**2 / K_not0**2)
+            cg_kz = (-N / K_not0) * ((KX / K_not0) * (KZ / K_not0))
+            freq_group = cg_kx.max() / oper.deltax + cg_kz.max() / oper.deltay
+            cp = N * (KX / K_not0**2)
+            freq_phase = cp.max() / oper.deltax
+            out["group_vel"] = self.cfl_coef_group / freq_group
+            out["phase_vel"] = 1.0 / freq_phase
+        return out
 
     # ------------------------------------------------------------------ observables
     def compute_energy(self):

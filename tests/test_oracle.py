@@ -139,6 +139,41 @@ def test_oracle_schemes_equal_reference_code(solver, shape, kw):
     assert not np.array_equal(ref_states[0], s0)
 
 
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("coef_group,forcing_rate", [(None, None), (1.0, None), (0.5, 8.0)])
+def test_cfl_rule_ns2d_strat_equals_reference_code(coef_group, forcing_rate):
+    """oracle CFL rule of ns2d.strat == the reference's TimeSteppingPseudoSpectralStrat
+    (_init_compute_time_step + _compute_time_increment_CFL_uxuyb, ns2d/strat/time_stepping.py:31-186)."""
+    refshim.install()
+    from fluidsim.solvers.ns2d.strat.time_stepping import TimeSteppingPseudoSpectralStrat
+
+    kw = dict(nu_2=1e-3, deltat0=0.2, N=3.0, Lx=8.0, Ly=6.0)
+    params = refshim.make_params("ns2d.strat", 32, 24, None, **kw)
+    params.time_stepping.USE_CFL = True
+    params.time_stepping._set_attrib("cfl_coef_group", coef_group)
+    if forcing_rate is not None:
+        params.forcing.enable = True
+        params.forcing._set_attrib("forcing_rate", forcing_rate)
+    ref = refshim.RefSim("ns2d.strat", params)
+    o = step_np.OracleSim("ns2d.strat", 32, 24, None, **kw)
+    o.cfl_coef_group, o.forcing_rate = coef_group, forcing_rate
+    o.init_noise(velo_max=0.05)
+    o.set_state_spect(with_buoyancy_2d(o, "ns2d.strat", 32, 24, kw))
+    ref.set_state_spect(np.array(o.state_spect))
+    ts = TimeSteppingPseudoSpectralStrat.__new__(TimeSteppingPseudoSpectralStrat)
+    ts.sim, ts.params = ref.sim, params
+    ts._init_compute_time_step()
+    lim = o.strat_time_increments()
+    assert ts.deltat_dispersion_relation == lim["dispersion_relation"]
+    if coef_group:
+        assert ts.deltat_group_vel == lim["group_vel"] and ts.deltat_phase_vel == lim["phase_vel"]
+    for scale in (1.0, 40.0, 41.0, 0.0):  # slow flow: a wave limit decides; fast flow: the advective CFL
+        o.set_state_spect(scale * np.array(o.state_spect) if scale else 0 * np.array(o.state_spect))
+        ref.set_state_spect(np.array(o.state_spect))
+        ts.compute_time_increment_CLF()
+        assert ts.deltat == o.compute_time_increment_CFL(cfl=ts.CFL, deltat_max=ts.deltat_max)
+
+
 def test_spectrum3d_sums_to_energy():
     """Shell spectrum (restated fluidfft compute_3dspectrum): sum(E(k)) * deltak == energy."""
     o = step_np.OracleSim("ns3d", 16, 12, 10, nu_2=1e-2, Lx=5.0)
