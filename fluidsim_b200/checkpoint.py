@@ -11,8 +11,9 @@ Mirror of ``PhysFieldsBase.save`` + ``save_file`` (``/root/reference/fluidsim/ba
                            (None stored as the string "None", fluiddyn's convention) + SAVE, NEW_DIR_RESULTS
 
 The file is plain HDF5 (``.h5``), the flavour the reference writes with an MPI-enabled h5py and reads with
-``h5py.File`` for every extension but ``.nc``.  It is produced by ``fluidsim_b200.minihdf5`` because
-h5py / libhdf5 are not available in this image (format parity unpinned, see that module).
+``h5py.File`` for every extension but ``.nc``.  It is written with h5py when that is importable, else by
+``fluidsim_b200.minihdf5`` -- the case in this image, where h5py / libhdf5 do not exist (format parity of
+that writer is unpinned, see the module).
 The state travels device -> host (``state_phys`` is float64 in X space, as in the reference) only here.
 """
 
@@ -23,7 +24,55 @@ import os
 import numpy as np
 import torch
 
-from .minihdf5 import read_hdf5, write_hdf5
+from . import minihdf5
+
+try:  # the reference's own container library, when the deployment has it
+    import h5py
+except ImportError:
+    h5py = None
+
+
+def _use_h5py():
+    return h5py is not None and os.environ.get("B2_MINIHDF5", "0") in ("0", "")
+
+
+def write_hdf5(path, root):
+    """Write the nested-dict tree (model of ``minihdf5``) with h5py when it is importable -- then the
+    file is libhdf5's own -- else with the built-in minimal writer."""
+    if not _use_h5py():
+        return minihdf5.write_hdf5(path, root)
+
+    def put(group, node):
+        for key, value in (node.get("@attrs") or {}).items():
+            group.attrs[key] = "None" if value is None else value
+        for name, child in node.items():
+            if name == "@attrs":
+                continue
+            if isinstance(child, dict):
+                put(group.create_group(name), child)
+            else:
+                group.create_dataset(name, data=child)
+
+    with h5py.File(str(path), "w") as h5file:
+        put(h5file, root)
+
+
+def read_hdf5(path):
+    if not _use_h5py():
+        return minihdf5.read_hdf5(path)
+
+    def get(group):
+        node = {}
+        attrs = dict(group.attrs.items())
+        if attrs:
+            node["@attrs"] = attrs
+        for name, item in group.items():
+            node[name] = get(item) if isinstance(item, h5py.Group) else item[...]
+        return node
+
+    with h5py.File(str(path), "r") as h5file:
+        return get(h5file)
+
 
 KEYS_PHYS_NEEDED = {
     "ns3d": ("vx", "vy", "vz"),  # solvers/ns3d/state.py:28
@@ -78,8 +127,8 @@ def tree_to_params(node, container):
             value = value.decode("utf-8")
         if isinstance(value, str) and value == "None":
             value = None
-        elif isinstance(value, np.ndarray) and value.dtype.kind == "S":
-            value = [v.decode("utf-8") for v in value.tolist()]
+        elif isinstance(value, np.ndarray) and value.dtype.kind in "SOU":
+            value = [v.decode("utf-8") if isinstance(v, bytes) else str(v) for v in value.tolist()]
         elif isinstance(value, np.generic):
             value = value.item()
         setattr(container, key, value)
