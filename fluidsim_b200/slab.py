@@ -77,6 +77,35 @@ def natural_from_exchanged(chunk, world, zc, nyl, nk, cyclic=False):
     return np.ascontiguousarray(b.transpose(1, 0, 2, 3)).reshape(zc, nyl * world, nk)
 
 
+def slab_layout(nx, ny, nz, rank, world, cyclic=False):
+    """Layout description of one rank in the vocabulary of a fluidfft MPI FFT class (what fluidsim reads
+    from ``oper_fft``: ``/root/reference/fluidsim/operators/operators3d.py:253-261,384-391``).
+
+    X side: z-slabs ``(nz/P, ny, nx)``; K side: ky-slabs stored ``(ny/P, nz, nx/2+1)``, ``dimX_K = (1, 0, 2)``.
+    With the block distribution the local ky rows are the contiguous block starting at
+    ``seq_indices_first_K[0]`` (the fftwmpi3d layout); with the cyclic one they are ``rank::P`` and
+    ``ky_indices_loc`` is the thing to use (``seq_indices_first_K`` then only names the first row)."""
+    check_divisible(nz, ny, world)
+    nyl, nzl, nk = ny // world, nz // world, nx // 2 + 1
+    ky_idx = np.arange(rank, ny, world) if cyclic else np.arange(rank * nyl, (rank + 1) * nyl)
+
+    def k_adim(n):
+        k = np.fft.fftfreq(n, 1.0 / n)
+        if n % 2 == 0:
+            k[n // 2] = n // 2
+        return k
+
+    return dict(
+        shapeX_seq=(nz, ny, nx), shapeX_loc=(nzl, ny, nx),
+        shapeK_seq=(ny, nz, nk), shapeK_loc=(nyl, nz, nk),
+        dimX_K=(1, 0, 2),
+        seq_indices_first_X=(rank * nzl, 0, 0),
+        seq_indices_first_K=(int(ky_idx[0]), 0, 0),
+        ky_indices_loc=ky_idx,
+        k_adim_loc=(k_adim(ny)[ky_idx], k_adim(nz), np.arange(nk, dtype=np.float64)),
+    )
+
+
 def check_divisible(nz, ny, world):
     if nz % world or ny % world:
         raise ValueError(f"slab decomposition needs nz={nz} and ny={ny} to be multiples of world={world}")
@@ -180,6 +209,34 @@ class SlabSimul:
         if os.environ.get("B2_SLAB_NATIVE", "1") not in ("0", "") and dist.get_backend(group) == "nccl":
             self._init_native_comm()
         self._dt_dev = self._vmax_dev = None
+
+    # ---- layout surface of a fluidfft MPI FFT class (operators3d.py:253-261) ------------------------
+    def layout(self):
+        return slab_layout(self.nx, self.ny, self.nz, self.rank, self.world, self.cyclic)
+
+    def get_shapeX_loc(self):
+        return self.layout()["shapeX_loc"]
+
+    def get_shapeX_seq(self):
+        return self.layout()["shapeX_seq"]
+
+    def get_shapeK_loc(self):
+        return self.layout()["shapeK_loc"]
+
+    def get_shapeK_seq(self):
+        return self.layout()["shapeK_seq"]
+
+    def get_dimX_K(self):
+        return self.layout()["dimX_K"]
+
+    def get_seq_indices_first_X(self):
+        return self.layout()["seq_indices_first_X"]
+
+    def get_seq_indices_first_K(self):
+        return self.layout()["seq_indices_first_K"]
+
+    def get_k_adim_loc(self):
+        return self.layout()["k_adim_loc"]
 
     def _init_native_comm(self):
         from ._lib import call, ptr

@@ -88,3 +88,31 @@ def test_divisibility_error():
 
     with pytest.raises(ValueError):
         check_divisible(10, 12, 4)
+
+
+def test_slab_layout_surface_matches_the_layout_algebra():
+    """slab_layout (the fluidfft MPI-class vocabulary: shapes, dimX_K, first indices, local k) agrees with
+    local_from_global for block and cyclic ky distributions."""
+    from fluidsim_b200.slab import global_from_local, local_from_global, slab_layout
+
+    nx, ny, nz, world = 8, 12, 6, 3
+    nk = nx // 2 + 1
+    ky = np.fft.fftfreq(ny, 1.0 / ny)
+    ky[ny // 2] = ny // 2
+    KY = np.broadcast_to(ky[None, :, None], (nz, ny, nk))  # sequential K array (nz, ny, nk)
+    for cyclic in (False, True):
+        parts = []
+        for rank in range(world):
+            lay = slab_layout(nx, ny, nz, rank, world, cyclic)
+            loc = local_from_global(KY, rank, world, cyclic)
+            assert loc.shape == lay["shapeK_loc"] == (ny // world, nz, nk)
+            assert lay["shapeX_loc"] == (nz // world, ny, nx) and lay["dimX_K"] == (1, 0, 2)
+            assert lay["seq_indices_first_X"] == (rank * (nz // world), 0, 0)
+            assert np.array_equal(loc[:, 0, 0], lay["k_adim_loc"][0])
+            assert lay["seq_indices_first_K"][0] == lay["ky_indices_loc"][0]
+            if not cyclic:  # fftwmpi3d blocks (operators3d.py:384-391)
+                assert lay["seq_indices_first_K"] == (rank * (ny // world), 0, 0)
+            parts.append(loc)
+        assert np.array_equal(global_from_local(parts, cyclic), KY)
+    with pytest.raises(ValueError):
+        slab_layout(8, 10, 6, 0, 4)
