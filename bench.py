@@ -619,7 +619,7 @@ def own_arm(args):
             ok = (world == 1 and free_dev > 2 * S.numel() * 16 + (6 << 30)
                   and host_mem_available() > 2 * S.numel() * 16)
             if ok:
-                nbatch = max(6, min(args.steps, 10))
+                nbatch = max(6, min(args.steps, 12))
                 pipe = e2e_pipelined(S, host, ts, sim, slab, nbatch, barrier)
         except Exception as exc:  # the serial figure above stands
             e2e["pipelined_note"] = f"pipelined run failed: {type(exc).__name__}: {str(exc)[:120]}"
