@@ -3,7 +3,8 @@
 Travels to the GPU box (no /root/reference there).  Each function cites the reference
 lines it follows; paths are relative to /root/reference/fluidsim.  Pinned here, in the
 build container, against the reference's own modules executed through
-``oracle.refshim`` (``tests/test_oracle_vs_reference.py``; fixtures in ``tests/golden``
+``oracle.refshim`` (``tests/test_oracle.py``, bit for bit, every solver and every time scheme;
+fixtures in ``tests/golden``
 made by ``tests/golden/make_golden.py``).  The fluidfft layer underneath
 (``oracle.fluidfft_np``) is a restatement of an absent third-party dependency:
 parity of that layer is UNPINNED (see ``oracle/__init__.py``).
