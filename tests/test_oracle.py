@@ -233,3 +233,91 @@ def test_oracle_spectra_and_means_are_consistent():
     o2.init_noise()
     m2 = o2.compute_spatial_means()
     assert abs(m2["epsK"] - 2 * 1e-2 * o2.compute_enstrophy()) < 1e-12 * m2["epsK"]
+
+
+# ------------------------------------------------------- invariants the reference's own tests assert
+def _with_b(o, solver, shape, kw):
+    """A state whose buoyancy field is non zero (the noise recipe of the 2-D solvers leaves b = 0)."""
+    s = np.array(o.state_spect)
+    if solver.startswith("ns2d"):
+        s = with_buoyancy_2d(o, solver, shape[0], shape[1], kw)
+    return s
+
+
+def test_nonlinear_term_conserves_energy_with_buoyancy():
+    """solvers/ns3d/strat/test_solver.py:26-58: sum Re(F_v . conj(v)) + Re(F_b conj(b)) / N^2 = 0."""
+    o = step_np.OracleSim("ns3d.strat", 32, 16, 16, N=1.7)
+    o.init_noise()
+    # the noise recipe low-passes b but does not truncate it (ns3d/init_fields.py:124-142); on this small
+    # grid the tail beyond the 2/3 cut-off is not negligible, and the identity needs a dealiased state
+    o.dealiasing(o.state_spect)
+    o.statephys_from_statespect()
+    T, S = np.array(o.tendencies_nonlin()), np.array(o.state_spect)
+    assert np.abs(S[3]).max() > 0
+    T_tot = sum(np.real(T[i].conj() * S[i]) for i in range(3)) + np.real(T[3].conj() * S[3]) / o.N**2
+    assert abs(o.oper.sum_wavenumbers(T_tot)) / o.oper.sum_wavenumbers(np.abs(T_tot)) < 1e-14
+
+
+def test_ns2d_nonlinear_term_conserves_enstrophy_and_energy():
+    """solvers/ns2d/test_solver.py:49-69: sum Re(conj(rot) F_rot) = 0 (enstrophy) and the same with the
+    1 / K^2 weight (energy), inviscid, beta = 0."""
+    o = step_np.OracleSim("ns2d", 48, 32, None, Lx=8.0, Ly=6.0)
+    o.init_noise()
+    rot = np.array(o.state_spect)[0]
+    F = np.array(o.tendencies_nonlin())[0]
+    sw = o.oper.sum_wavenumbers
+    T = np.real(rot.conj() * F)
+    assert abs(sw(T)) / sw(np.abs(T)) < 1e-14
+    TE = T / o.oper.K2_not0
+    assert abs(sw(TE)) / sw(np.abs(TE)) < 1e-14
+
+
+@pytest.mark.parametrize("solver", ["ns2d.strat", "ns2d.bouss"])
+def test_ns2d_buoyancy_solvers_conserve_energy(solver):
+    """Simul.check_energy_conservation of ns2d.strat (solvers/ns2d/strat/solver.py:183-213):
+    d/dt (E_K + E_A) = 0 for the inviscid tendencies, E_A = |b|^2 / (2 N^2).  ns2d.bouss has no
+    background stratification: only the advective part of its terms is energy-neutral, checked as
+    enstrophy-like invariance of b (sum Re(conj(b) F_b) = 0)."""
+    kw = dict(N=1.3, Lx=8.0, Ly=6.0) if solver == "ns2d.strat" else dict(Lx=8.0, Ly=6.0)
+    o = step_np.OracleSim(solver, 48, 32, None, **kw)
+    o.init_noise()
+    o.set_state_spect(_with_b(o, solver, (48, 32), kw))
+    S, T = np.array(o.state_spect), np.array(o.tendencies_nonlin())
+    sw = o.oper.sum_wavenumbers
+    if solver == "ns2d.strat":
+        division = 1.0 / o.oper.K2_not0
+        division[0, 0] = 0
+        pt = 0.5 * division * np.real(S[0].conj() * T[0]) + np.real(S[1].conj() * T[1]) / (2 * o.N**2)
+    else:
+        pt = np.real(S[1].conj() * T[1])
+    assert abs(sw(pt)) / sw(np.abs(pt)) < 1e-14
+
+
+@pytest.mark.parametrize(
+    "scheme,order",
+    [("Euler", 1), ("Euler_phaseshift", 1), ("RK2", 2), ("RK2_trapezoid", 2), ("RK2_phaseshift", 2),
+     ("RK2_phaseshift_exact", 2), ("RK4", 4)],
+)
+def test_time_schemes_converge_at_their_order(scheme, order):
+    """The counterpart of the reference's nl1d exact-solution test (solvers/nl1d/test_solver.py:56-163)
+    on the hot-path solvers: halving the time step divides the error (against a fine RK4 run) by
+    2^order."""
+    kw = dict(nu_2=5e-2, Lx=2 * np.pi, Ly=2 * np.pi)
+    init = step_np.OracleSim("ns2d", 32, 32, None, **kw)
+    init.init_noise()
+    s0 = np.array(init.state_spect)
+    t_end = 0.4
+
+    def run(sch, nsteps):
+        o = step_np.OracleSim("ns2d", 32, 32, None, deltat0=t_end / nsteps, type_time_scheme=sch, **kw)
+        o.set_state_spect(s0)
+        for _ in range(nsteps):
+            o.one_time_step()
+        return np.array(o.state_spect)
+
+    exact = run("RK4", 512)
+    e1 = np.abs(run(scheme, 16) - exact).max()
+    e2 = np.abs(run(scheme, 32) - exact).max()
+    assert e1 > 1e-12  # resolvable error
+    measured = np.log2(e1 / e2)
+    assert order - 0.35 < measured < order + 0.6, (measured, e1, e2)
