@@ -100,65 +100,64 @@ class _StubForcing:
         pass
 
 
+def generate(name):
+    """Run the reference for one case; returns (meta dict, dict of arrays) -- what main() stores."""
+    solver, shape, nsteps, kw = CASES[name]
+    nx, ny = shape[0], shape[1]
+    nz = shape[2] if len(shape) == 3 else None
+    # initial condition: the reference's noise recipe (restated in step_np.init_noise, which
+    # is itself checked against the reference in tests/test_oracle.py)
+    kw = dict(kw)
+    random_seed = kw.pop("random_seed", None)
+    scheme = kw.get("type_time_scheme", "RK4")
+    okw = dict(kw)
+    if scheme not in ("RK2", "RK4"):
+        okw["type_time_scheme"] = "RK4"  # the oracle only provides the initial state here
+    o = step_np.OracleSim(solver, nx, ny, nz, **okw)
+    o.init_noise()
+    s0 = np.array(o.state_spect)
+    if solver in ("ns2d.strat", "ns2d.bouss"):
+        o2 = step_np.OracleSim(solver, nx, ny, nz, **okw)
+        o2.init_noise(seed=7)
+        s0[1] = 0.5 * np.array(o2.state_spect)[0]
+    params = refshim.make_params(solver, nx, ny, nz, **kw)
+    if random_seed is not None:
+        import random
+
+        random.seed(random_seed)
+    ref = refshim.RefSim(solver, params)
+    ref.set_state_spect(s0)
+    extra = {}
+    if name.endswith("_forced"):
+        forcing = make_forcing(o)
+        sov = type(ref.sim.state.state_spect)(like=ref.sim.state.state_spect, value=0.0)
+        sov[...] = forcing
+        ref.sim.is_forcing_enabled = True
+        ref.sim.params.forcing.enable = True
+        ref.sim.forcing = _StubForcing(sov)
+        extra["forcing"] = forcing
+    mask = np.array(ref.oper.where_dealiased)
+    tend0 = np.array(ref.sim.tendencies_nonlin())
+    states = []
+    for _ in range(nsteps):
+        states.append(ref.step())
+    e = step_np.OracleSim(solver, nx, ny, nz, **okw)
+    e.set_state_spect(states[-1])
+    meta = dict(solver=solver, shape=shape, nsteps=nsteps, params=kw,
+                **({} if random_seed is None else {"random_seed": random_seed}))
+    arrays = dict(state0=s0, mask=mask, tend0=tend0, state1=states[0], stateN=states[-1],
+                  energyN=e.compute_energy(), enstrophyN=e.compute_enstrophy(), **extra)
+    return meta, arrays
+
+
 def main():
     outdir = os.path.dirname(os.path.abspath(__file__))
-    for name, (solver, shape, nsteps, kw) in CASES.items():
+    for name in CASES:
         if os.path.exists(os.path.join(outdir, name + ".npz")) and "--all" not in sys.argv:
             continue  # committed fixtures are kept byte-identical; --all regenerates everything
-        nx, ny = shape[0], shape[1]
-        nz = shape[2] if len(shape) == 3 else None
-        # initial condition: the reference's noise recipe (restated in step_np.init_noise, which
-        # is itself checked against the reference in tests/test_oracle.py)
-        kw = dict(kw)
-        random_seed = kw.pop("random_seed", None)
-        scheme = kw.get("type_time_scheme", "RK4")
-        okw = dict(kw)
-        if scheme not in ("RK2", "RK4"):
-            okw["type_time_scheme"] = "RK4"  # the oracle only provides the initial state here
-        o = step_np.OracleSim(solver, nx, ny, nz, **okw)
-        o.init_noise()
-        s0 = np.array(o.state_spect)
-        if solver in ("ns2d.strat", "ns2d.bouss"):
-            o2 = step_np.OracleSim(solver, nx, ny, nz, **okw)
-            o2.init_noise(seed=7)
-            s0[1] = 0.5 * np.array(o2.state_spect)[0]
-        params = refshim.make_params(solver, nx, ny, nz, **kw)
-        if random_seed is not None:
-            import random
-
-            random.seed(random_seed)
-        ref = refshim.RefSim(solver, params)
-        ref.set_state_spect(s0)
-        extra = {}
-        if name.endswith("_forced"):
-            forcing = make_forcing(o)
-            sov = type(ref.sim.state.state_spect)(like=ref.sim.state.state_spect, value=0.0)
-            sov[...] = forcing
-            ref.sim.is_forcing_enabled = True
-            ref.sim.params.forcing.enable = True
-            ref.sim.forcing = _StubForcing(sov)
-            extra["forcing"] = forcing
-        mask = np.array(ref.oper.where_dealiased)
-        tend0 = np.array(ref.sim.tendencies_nonlin())
-        states = []
-        for _ in range(nsteps):
-            states.append(ref.step())
-        e = step_np.OracleSim(solver, nx, ny, nz, **okw)
-        e.set_state_spect(states[-1])
-        np.savez_compressed(
-            os.path.join(outdir, name + ".npz"),
-            meta=json.dumps(dict(solver=solver, shape=shape, nsteps=nsteps, params=kw,
-                                 **({} if random_seed is None else {"random_seed": random_seed}))),
-            state0=s0,
-            mask=mask,
-            tend0=tend0,
-            state1=states[0],
-            stateN=states[-1],
-            energyN=e.compute_energy(),
-            enstrophyN=e.compute_enstrophy(),
-            **extra,
-        )
-        print(name, "ok", s0.shape)
+        meta, arrays = generate(name)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), meta=json.dumps(meta), **arrays)
+        print(name, "ok", arrays["state0"].shape)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,7 @@
 """CPU tests: the numpy oracle against the committed golden vectors and (in the build container)
 against the reference's own modules executed through ``oracle.refshim``."""
+import os
+
 import numpy as np
 import pytest
 
@@ -321,3 +323,24 @@ def test_time_schemes_converge_at_their_order(scheme, order):
     assert e1 > 1e-12  # resolvable error
     measured = np.log2(e1 / e2)
     assert order - 0.35 < measured < order + 0.6, (measured, e1, e2)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", all_golden_cases())
+def test_committed_goldens_reproduce_from_the_reference_code(name):
+    """Every committed fixture is what the reference's own modules produce today (same script, same
+    inputs): guards against a stale or hand-edited golden."""
+    import importlib.util
+    import json
+
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    )
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    assert set(mg.CASES) == set(all_golden_cases())
+    meta, arrays = mg.generate(name)
+    stored_meta, z = load_golden(name)
+    assert json.loads(json.dumps(meta)) == stored_meta
+    for key, value in arrays.items():
+        assert np.array_equal(np.asarray(value), z[key]), key
