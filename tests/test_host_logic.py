@@ -139,3 +139,74 @@ def test_pyproject_entry_points_resolve():
             p = Simul.create_default_params()
             assert p.time_stepping.type_time_scheme == "RK4"
             assert hasattr(Simul, "InfoSolver") and hasattr(Simul, "tendencies_nonlin")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("cyclic", [False, True])
+@pytest.mark.parametrize("nchunks", [1, 2])
+def test_pruned_exchange_formulas_for_every_world_size(world, cyclic, nchunks):
+    """Formula-level emulation of one pruned global transpose, K side -> z-slab side, for 2 / 4 / 8 ranks:
+    the z-inverse pass stores through ``SlabMapper`` (csrc/strided.cu), the all-to-all moves the per-peer
+    blocks of ``SlabSimul._exchange_plan``, the y-inverse pass loads through ``RowMap::xoff``
+    (csrc/passes.cuh) with the per-rank bands of ``b2i_slab_local_band`` (csrc/api.cu, =
+    ``SlabSimul._local_band``).  Restated here in numpy; every kept (ky, z, kx) must arrive where the
+    y pass looks for it."""
+    from fluidsim_b200.slab import SlabSimul
+
+    ny, nz, nk, keepx = 32, 16, 9, 6
+    gy_lo, gy_hi = 11, 22  # global dealiased ky band
+    nyl, nzl = ny // world, nz // world
+    if nzl % nchunks:
+        pytest.skip("chunks do not divide the local z range")
+    zc = nzl // nchunks
+    pitch = keepx
+    fake = _FakeSlab(ny, world, cyclic)
+    bands = [SlabSimul._local_band(fake, r, gy_lo, gy_hi) for r in range(world)]
+    nkr = [nyl - (hi - lo) for lo, hi in bands]
+    cs_a = ny * zc * pitch        # chunk stride of a K-side send buffer (SlabMapper::cstride)
+    cs_b = sum(nkr) * zc * pitch  # chunk stride of a z-slab-side receive buffer (cs_x in b2i_slab_ypass)
+    blk = np.concatenate([[0], np.cumsum([n * zc * pitch for n in nkr])])  # RowMap::blk
+
+    def ident(g, z, kx):  # unique value of mode (global ky row g, z, kx)
+        return (g * nz + z) * nk + kx
+
+    def grow(r, yl):  # global ky row of local row yl of rank r
+        return yl * world + r if cyclic else r * nyl + yl
+
+    # z-inverse store on every rank s (SlabMapper::operator())
+    send = [np.full(nchunks * cs_a, -1.0) for _ in range(world)]
+    for s in range(world):
+        lo, hi = bands[s]
+        gap = hi - lo
+        for yl in range(nyl):
+            if lo <= yl < hi:
+                continue  # dealiased row: not visited
+            ylc = yl if yl < lo else yl - gap
+            for z in range(nz):
+                q, zl = divmod(z, nzl)
+                c, zlc = divmod(zl, zc)
+                base = c * cs_a + ((q * zc + zlc) * nkr[s] + ylc) * pitch
+                send[s][base:base + pitch] = ident(grow(s, yl), z, np.arange(pitch))
+    # all-to-all per chunk: rank s -> peer q, equal blocks of nkr[s] * zc * pitch ("mine" / "theirs")
+    recv = [np.full(nchunks * cs_b, -1.0) for _ in range(world)]
+    for c in range(nchunks):
+        for s in range(world):
+            n = nkr[s] * zc * pitch
+            for q in range(world):
+                recv[q][c * cs_b + blk[s]: c * cs_b + blk[s] + n] = send[s][c * cs_a + q * n: c * cs_a + (q + 1) * n]
+    # y-inverse load on every rank q (RowMap::xoff)
+    d = world if cyclic else nyl
+    for q in range(world):
+        assert (recv[q] >= 0).all()  # every slot of the receive buffer was written
+        for c in range(nchunks):
+            for i in range(ny):
+                if gy_lo <= i < gy_hi:
+                    continue  # band rows are never loaded
+                qq, m = divmod(i, d)
+                r, yl = (m, qq) if cyclic else (qq, m)
+                lo, hi = bands[r]
+                ylc = yl if yl < lo else yl - (hi - lo)
+                for zlc in range(zc):
+                    off = c * cs_b + blk[r] + (zlc * nkr[r] + ylc) * pitch
+                    z = q * nzl + c * zc + zlc
+                    assert np.array_equal(recv[q][off:off + pitch], ident(i, z, np.arange(pitch))), (q, c, i, zlc)
